@@ -1,0 +1,243 @@
+// extern "C" entry points of libtinygemm_b200.so: argument validation (the reference's
+// TORCH_CHECKs restated on plain sizes), format dispatch, error strings.
+// Declarations and the reference interface each one replaces: include/tinygemm_b200.h.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace tg {
+
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += (uint64_t)n; }
+
+int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
+                        const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
+                        tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st);
+int launch_gemm_w4_rm_A(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
+                        const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
+                        tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st);
+
+namespace {
+
+// int4 and mx4 run through the LUT kernels with a constant table per dtype
+// (reference: Dequantization.cuh:136-260 "code - 8", FloatDefs.cuh:18-34 kMX4_Values)
+__device__ uint16_t g_const_luts[4][16];  // [int4 bf16, int4 fp16, mx4 bf16, mx4 fp16]
+
+__global__ void init_const_luts_kernel() {
+  const int i = threadIdx.x;
+  if (i < 16) {
+    const float mx[16] = {0.f, .5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f, -0.f, -.5f, -1.f, -1.5f, -2.f, -3.f, -4.f, -6.f};
+    g_const_luts[0][i] = __bfloat16_as_ushort(__float2bfloat16_rn((float)(i - 8)));
+    g_const_luts[1][i] = __half_as_ushort(__float2half_rn((float)(i - 8)));
+    g_const_luts[2][i] = __bfloat16_as_ushort(__float2bfloat16_rn(mx[i]));
+    g_const_luts[3][i] = __half_as_ushort(__float2half_rn(mx[i]));
+  }
+}
+
+// Returns the device address of the constant LUT for (fmt, dt); on first use per
+// (thread, device) the table is filled by a 1-warp kernel ordered on the caller's stream.
+int const_lut_for(tg_w4_format fmt, tg_dtype dt, cudaStream_t st, const uint16_t** out) {
+  constexpr int kMaxDev = 64;
+  static thread_local const uint16_t* base[kMaxDev] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) {
+    set_error("no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    return TG_ERR_CUDA;
+  }
+  if (base[dev] == nullptr) {
+    uint16_t* p = nullptr;
+    if (cudaGetSymbolAddress((void**)&p, g_const_luts) != cudaSuccess) {
+      set_error("cudaGetSymbolAddress failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return TG_ERR_CUDA;
+    }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    (void)cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone) {
+      // filling the table inside a capture would bake a one-off init into the graph
+      set_error("first int4/mx4 call on this device must happen outside CUDA graph capture");
+      return TG_ERR_UNSUPPORTED;
+    }
+    init_const_luts_kernel<<<1, 32, 0, st>>>();
+    TG_CHECK_LAUNCH("init_const_luts");
+    base[dev] = p;
+  }
+  *out = base[dev] + ((fmt == TG_W4_MX4 ? 2 : 0) + (dt == TG_FP16 ? 1 : 0)) * 16;
+  return TG_OK;
+}
+
+bool valid_group(int g) { return g == 32 || g == 64 || g == 128 || g == 256; }
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_common(const char* fn, const void* y, const void* x, const void* w, int64_t rows_x, int64_t w_rows,
+                 int64_t k, tg_weight_side side, tg_dtype dt) {
+  TG_REQUIRE(y && x && w, "%s: null tensor pointer", fn);
+  TG_REQUIRE(dt == TG_BF16 || dt == TG_FP16, "%s: dtype must be bf16 or fp16", fn);
+  TG_REQUIRE(side == TG_WEIGHT_A || side == TG_WEIGHT_B, "%s: bad weight side", fn);
+  TG_REQUIRE(rows_x >= 0 && w_rows > 0 && k > 0, "%s: bad sizes rows_x=%lld w_rows=%lld k=%lld", fn, (long long)rows_x,
+             (long long)w_rows, (long long)k);
+  TG_REQUIRE(k % 32 == 0, "%s: k (%lld) must be a multiple of 32", fn, (long long)k);
+  const int rt = side == TG_WEIGHT_A ? 16 : 8;
+  TG_REQUIRE(w_rows % rt == 0, "%s: padded weight rows (%lld) must be a multiple of %d", fn, (long long)w_rows, rt);
+  TG_REQUIRE(k < (1ll << 30) && w_rows < (1ll << 30) && rows_x < (1ll << 30), "%s: sizes exceed 32-bit indexing", fn);
+  TG_REQUIRE(aligned16(x) && aligned16(w) && (reinterpret_cast<uintptr_t>(y) & 1u) == 0,
+             "%s: x and w must be 16-byte aligned", fn);
+  return TG_OK;
+}
+
+}  // namespace
+}  // namespace tg
+
+using namespace tg;
+
+extern "C" {
+
+const char* tg_last_error(void) { return g_err; }
+const char* tg_version(void) { return "tinygemm_b200 0.1 sm_100a"; }
+uint64_t tg_launch_count(void) { return g_launches; }
+void tg_reset_launch_count(void) { g_launches = 0; }
+
+int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
+                  const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
+                  int inner_k_tiles, tg_w4_format format, tg_weight_side side, tg_dtype dtype, void* stream) {
+  const char* fn = "tg_gemm_w4_rm";
+  int rc = check_common(fn, y, x, w, rows_x, w_rows, k, side, dtype);
+  if (rc != TG_OK) return rc;
+  TG_REQUIRE(format >= TG_W4_INT4 && format <= TG_W4_MX4, "%s: bad format", fn);
+  TG_REQUIRE(valid_group(group), "%s: qGroupSize must be 32, 64, 128 or 256 (got %d)", fn, group);
+  TG_REQUIRE(k % group == 0, "%s: k (%lld) must be a multiple of qGroupSize (%d)", fn, (long long)k, group);
+  const int ik = inner_k_tiles;
+  if (side == TG_WEIGHT_B) {
+    TG_REQUIRE(ik == 2 || ik == 4 || ik == 8, "%s: B-layout innerKTiles must be 2, 4 or 8 (got %d)", fn, ik);
+  } else {
+    TG_REQUIRE(ik == 1 || ik == 2 || ik == 4, "%s: A-layout innerKTiles must be 1, 2 or 4 (got %d)", fn, ik);
+  }
+  TG_REQUIRE((k / 16) % ik == 0, "%s: k/16 (%lld) must be a multiple of innerKTiles (%d)", fn, (long long)(k / 16), ik);
+  if (format == TG_W4_MX4) {
+    TG_REQUIRE(exponents != nullptr, "%s: mx4 needs exponents", fn);
+    if (dtype != TG_BF16) {
+      set_error("%s: mx4 supports bf16 activations only", fn);
+      return TG_ERR_UNSUPPORTED;
+    }
+  } else {
+    TG_REQUIRE(scales_zeros != nullptr && aligned16(scales_zeros), "%s: scales_zeros missing or not 16-byte aligned", fn);
+  }
+  if (format == TG_W4_ANY4_GLOBAL || format == TG_W4_ANY4_ROWWISE) {
+    TG_REQUIRE(lut != nullptr && aligned16(lut), "%s: any4 LUT missing or not 16-byte aligned", fn);
+  }
+  if (rows_x == 0) return TG_OK;
+  const uint16_t* clut = nullptr;
+  if (format == TG_W4_INT4 || format == TG_W4_MX4) {
+    rc = const_lut_for(format, dtype, (cudaStream_t)stream, &clut);
+    if (rc != TG_OK) return rc;
+  }
+  if (side == TG_WEIGHT_B) {
+    return launch_gemm_w4_rm_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
+                               (cudaStream_t)stream);
+  }
+  return launch_gemm_w4_rm_A(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
+                             (cudaStream_t)stream);
+}
+
+int tg_gemm_w8_rm(void* y, const void* x, const int32_t* w, const void* scales_zeros, int64_t rows_x,
+                  int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_weight_side side, tg_dtype dtype,
+                  void* stream) {
+  const char* fn = "tg_gemm_w8_rm";
+  int rc = check_common(fn, y, x, w, rows_x, w_rows, k, side, dtype);
+  if (rc != TG_OK) return rc;
+  TG_REQUIRE(valid_group(group), "%s: qGroupSize must be 32, 64, 128 or 256 (got %d)", fn, group);
+  TG_REQUIRE(k % group == 0, "%s: k (%lld) must be a multiple of qGroupSize (%d)", fn, (long long)k, group);
+  TG_REQUIRE(scales_zeros != nullptr, "%s: scales_zeros missing", fn);
+  const int ik = inner_k_tiles;
+  if (side == TG_WEIGHT_B) {
+    TG_REQUIRE(ik == 1 || ik == 2 || ik == 4, "%s: B-layout innerKTiles must be 1, 2 or 4 (got %d)", fn, ik);
+  } else {
+    TG_REQUIRE(ik == 1 || ik == 2, "%s: A-layout innerKTiles must be 1 or 2 (got %d)", fn, ik);
+  }
+  TG_REQUIRE((k / 16) % ik == 0, "%s: k/16 must be a multiple of innerKTiles (%d)", fn, ik);
+  if (rows_x == 0) return TG_OK;
+  return launch_gemm_w8_rm(y, x, w, scales_zeros, rows_x, w_rows, k, group, ik, side, dtype, (cudaStream_t)stream);
+}
+
+int tg_gemm_w16_rm(void* y, const void* x, const void* w, int64_t rows_x, int64_t w_rows, int64_t k,
+                   int inner_k_tiles, tg_weight_side side, tg_dtype dtype, void* stream) {
+  const char* fn = "tg_gemm_w16_rm";
+  int rc = check_common(fn, y, x, w, rows_x, w_rows, k, side, dtype);
+  if (rc != TG_OK) return rc;
+  const int ik = inner_k_tiles;
+  if (side == TG_WEIGHT_B) {
+    TG_REQUIRE(ik == 1 || ik == 2, "%s: B-layout innerKTiles must be 1 or 2 (got %d)", fn, ik);
+  } else {
+    TG_REQUIRE(ik == 1, "%s: A-layout innerKTiles must be 1 (got %d)", fn, ik);
+  }
+  TG_REQUIRE((k / 16) % ik == 0, "%s: k/16 must be a multiple of innerKTiles (%d)", fn, ik);
+  if (rows_x == 0) return TG_OK;
+  return launch_gemm_w16_rm(y, x, w, rows_x, w_rows, k, ik, side, dtype, (cudaStream_t)stream);
+}
+
+// ---- tensor-core-layout activations / outputs: RM staging in the caller's workspace ----
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t tg_gemm_tc_workspace_bytes(int64_t rows_x, int64_t w_rows, int64_t k) {
+  return align256((size_t)rows_x * (size_t)k * 2) + align256((size_t)rows_x * (size_t)w_rows * 2);
+}
+
+// unpack x (A layout when the weight is on the right, B layout otherwise) into the workspace
+static int tc_unpack_x(const void* x, void* xs, int64_t rows_x, int64_t k, int x_ik, tg_weight_side side, void* stream) {
+  if (side == TG_WEIGHT_B) return tg_convert_from_A(x, xs, rows_x, k, stream);
+  return tg_convert_from_B(x, xs, rows_x, k, x_ik, stream);
+}
+// pack y [rows_x][w_rows] into the layout of the activation operand
+static int tc_pack_y(const void* ys, void* y, int64_t rows_x, int64_t w_rows, int x_ik, tg_weight_side side, void* stream) {
+  if (side == TG_WEIGHT_B) return tg_convert_to_A(ys, y, rows_x, w_rows, stream);
+  return tg_convert_to_B(ys, y, rows_x, w_rows, x_ik, stream);
+}
+
+#define TG_TC_PROLOGUE(fn)                                                                         \
+  TG_REQUIRE(workspace != nullptr && aligned16(workspace), "%s: workspace missing or misaligned", fn); \
+  TG_REQUIRE(x_inner_k_tiles == 1 || (side == TG_WEIGHT_A && x_inner_k_tiles == 2),                \
+             "%s: bad activation innerKTiles %d", fn, x_inner_k_tiles);                            \
+  TG_REQUIRE(rows_x % (side == TG_WEIGHT_B ? 16 : 8) == 0, "%s: rows_x must be padded to the tile size", fn); \
+  char* xs = (char*)workspace;                                                                     \
+  char* ys = xs + align256((size_t)rows_x * (size_t)k * 2);                                        \
+  if (rows_x == 0) return TG_OK;                                                                   \
+  int rc = tc_unpack_x(x, xs, rows_x, k, x_inner_k_tiles, side, stream);                           \
+  if (rc != TG_OK) return rc;
+
+int tg_gemm_w4_tc(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
+                  const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
+                  int inner_k_tiles, int x_inner_k_tiles, tg_w4_format format, tg_weight_side side,
+                  tg_dtype dtype, void* workspace, void* stream) {
+  TG_TC_PROLOGUE("tg_gemm_w4_tc");
+  rc = tg_gemm_w4_rm(ys, xs, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, inner_k_tiles, format, side,
+                     dtype, stream);
+  if (rc != TG_OK) return rc;
+  return tc_pack_y(ys, y, rows_x, w_rows, x_inner_k_tiles, side, stream);
+}
+
+int tg_gemm_w8_tc(void* y, const void* x, const int32_t* w, const void* scales_zeros, int64_t rows_x,
+                  int64_t w_rows, int64_t k, int group, int inner_k_tiles, int x_inner_k_tiles,
+                  tg_weight_side side, tg_dtype dtype, void* workspace, void* stream) {
+  TG_TC_PROLOGUE("tg_gemm_w8_tc");
+  rc = tg_gemm_w8_rm(ys, xs, w, scales_zeros, rows_x, w_rows, k, group, inner_k_tiles, side, dtype, stream);
+  if (rc != TG_OK) return rc;
+  return tc_pack_y(ys, y, rows_x, w_rows, x_inner_k_tiles, side, stream);
+}
+
+int tg_gemm_w16_tc(void* y, const void* x, const void* w, int64_t rows_x, int64_t w_rows, int64_t k,
+                   int inner_k_tiles, int x_inner_k_tiles, tg_weight_side side, tg_dtype dtype,
+                   void* workspace, void* stream) {
+  TG_TC_PROLOGUE("tg_gemm_w16_tc");
+  rc = tg_gemm_w16_rm(ys, xs, w, rows_x, w_rows, k, inner_k_tiles, side, dtype, stream);
+  if (rc != TG_OK) return rc;
+  return tc_pack_y(ys, y, rows_x, w_rows, x_inner_k_tiles, side, stream);
+}
+
+}  // extern "C"

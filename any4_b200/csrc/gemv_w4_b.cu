@@ -1,0 +1,600 @@
+// B200 (sm_100a) weight-only 4-bit GEMV/small-batch GEMM, weight in the reference's "B" int4
+// tensor-core layout (weightOnRight = true, the Any4Linear default).
+//
+// Replaces the reference path tinygemm_y_f16RM_x_f16RM_w_{int4,any4,mx4}TC ->
+// tinygemm_m16n8k16_chunk_kernel<ALayout_RM, BLayout_TC_int4> (TinyGemm_int4.cu:294-548,
+// TinyGemmImpl.cuh:23-345, MatrixLayoutB.cuh:686-1101, Dequantization.cuh:55-131).
+// It is NOT a port of that gmem->register kernel.  Design (see DESIGN.md for the budget):
+//
+//  * "Lane per weight row".  A CTA owns 32 consecutive weight rows (4 n-tiles of the packed
+//    layout, one contiguous run of bytes) and lane L of EVERY warp works on row L; the warps
+//    split k.  The per-row 16-entry LUT is expanded once per CTA into a 256-entry *byte pair*
+//    table  pair[b] = (LUT[b & 15], LUT[b >> 4])  stored bank-private (row L only ever touches
+//    shared-memory bank L), so the two nibbles of a packed byte are dequantised by ONE
+//    conflict-free LDS.32 whose address is ONE PRMT (table at a 64 KiB-aligned shared address,
+//    256-byte entry pitch, so `byte << 8 | lane*4 | base` is a byte permute).
+//  * Group scale/zero are applied with one fma.rn.{bf16,f16}x2 per pair - the same single
+//    rounded FMA as the reference (MatrixLayoutB.cuh:1042-1046), so every dequantised weight
+//    is bit-identical to the reference's.
+//  * Weights stream HBM -> shared memory with 1-D bulk TMA (cp.async.bulk + mbarrier
+//    complete_tx) into warp-private multi-stage rings: no CTA-wide barrier in the k loop.
+//  * The dot products go to the tensor pipe (mma.sync m16n8k16, fp32 accumulate) even at m = 1
+//    so the FMA pipe stays free for the dequant.  Because all 32 lanes hold DIFFERENT weight
+//    rows, the activation operand is block-structured: x sits in k-slots {2q,2q+1,2q+8,2q+9}
+//    of operand column/row q only, which makes output entry (g, q) the dot product of lane
+//    4g+q's row.  At m = 1 the second half of the A fragment carries a second k-set of the
+//    same rows (256 useful MACs per HMMA); for m > 1 the weights are the B fragment and four
+//    activation rows ride in one HMMA.
+//  * Split-k for small n uses a thread-block cluster and a DSMEM reduction (no workspace).
+//
+// Numerics: dequantised weights bit-identical to the reference; products exact; fp32
+// accumulation (order differs from the reference, as allowed by SURVEY.md 3.6); one RN at
+// the end.  Non-finite weights (mx4 exponent 255) additionally poison the up to three other
+// rows that share an mma row with them (0 * NaN); the reference confines the NaN to its row.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace tg {
+namespace {
+
+constexpr int kWarps = 8;              // consumer warps per CTA (all warps consume)
+constexpr int kThreads = kWarps * 32;
+constexpr int kStages = 3;             // ring depth per warp
+constexpr int kRowsPerCta = 32;        // = 4 n-tiles
+constexpr int kChunkK = 128;           // k elements per ring stage
+constexpr int kTileChunkBytes = 512;   // bytes of one n-tile (8 rows) per stage: 8 * 128 / 2
+constexpr int kStageWBytes = 4 * kTileChunkBytes;
+constexpr uint32_t kTableBase = 0x10000u;       // shared-window address of the pair table (64 KiB aligned)
+constexpr uint32_t kTableBytes = 0x10000u;      // 256 entries * 256 B pitch
+constexpr uint32_t kXBase = kTableBase + 128u;  // activations live in the unused half of each 256 B line
+constexpr uint32_t kRedBase = kTableBase + kTableBytes;  // cross-warp reduction scratch
+constexpr uint32_t kRedBytes = kWarps * 4 * 32 * 4;      // [warp][4][32] fp32
+constexpr uint32_t kDynSmemBytes = kRedBase + kRedBytes; // requested dynamic smem (window base <= 1024)
+constexpr int kMaxXBytes = 32768;      // capacity of the activation area
+
+struct Params {
+  const uint8_t* w;      // packed weight
+  const uint16_t* x;     // [m][k]
+  uint16_t* y;           // [m][w_rows]
+  const uint32_t* sz;    // [k/g][w_rows] (scale, zero) pairs, null for mx4
+  const uint8_t* exps;   // [w_rows][k/g] e8m0, mx4 only
+  const uint16_t* lut;   // [16] or [w_rows][16]
+  int lut_stride;        // 0 or 16
+  int m;                 // activation rows handled by this launch (1 for the M1 kernel, <= 4 otherwise)
+  int w_rows;            // padded weight rows (multiple of 8)
+  int k;
+  int glog2;             // log2(group)
+  int64_t tile_stride;   // bytes between consecutive n-tiles of the packed weight = 4 * k
+  int64_t y_stride;      // elements between activation rows of y (= total w_rows)
+  int x_row_bytes;       // staged bytes per activation row, multiple of 128
+  int splits;            // cluster size along k (gridDim.y)
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v));
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b));
+}
+// predicated 8-byte shared load; lanes with p == 0 keep the previous register contents (zero)
+__device__ __forceinline__ void lds64_if(uint32_t& a, uint32_t& b, uint32_t addr, uint32_t p) {
+  asm volatile(
+      "{ .reg .pred pp; setp.ne.u32 pp, %3, 0; @pp ld.shared.v2.b32 {%0,%1}, [%2]; }"
+      : "+r"(a), "+r"(b)
+      : "r"(addr), "r"(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk TMA global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <tg_dtype DT>
+__device__ __forceinline__ uint32_t fma2(uint32_t v, uint32_t s, uint32_t z) {
+  uint32_t r;
+  if constexpr (DT == TG_BF16) {
+    asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(s), "r"(z));
+  } else {
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(s), "r"(z));
+  }
+  return r;
+}
+
+template <tg_dtype DT>
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  if constexpr (DT == TG_BF16) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+}
+
+template <tg_dtype DT>
+__device__ __forceinline__ uint16_t f32_to_dt(float f) {
+  if constexpr (DT == TG_BF16) {
+    return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  } else {
+    return __half_as_ushort(__float2half_rn(f));
+  }
+}
+
+// e8m0 -> dtype bits: 2^(e-127), 255 -> NaN (reference: Dequantization.cuh:331-351)
+template <tg_dtype DT>
+__device__ __forceinline__ uint32_t e8m0_to_dt(uint32_t e) {
+  if constexpr (DT == TG_BF16) {
+    if (e == 255u) return 0x7fc0u;
+    if (e == 0u) return 0x0040u;  // 2^-127 is a bf16 subnormal
+    return e << 7;
+  } else {
+    return (uint32_t)__half_as_ushort(__float2half_rn(e == 255u ? __int_as_float(0x7fc00000) : exp2f((float)e - 127.0f)));
+  }
+}
+
+// Static description of the packed words one lane owns in a 16-byte "unit" of its row's
+// stage slice: word i of unit u covers k-slot q and tile pair tp (k-tiles 2tp, 2tp+1 of the
+// stage).  See the B int4 layout [n/8][k/(ik*16)][32][ik/2] (TinyGemmConvertB.cu:252-308).
+template <int IK>
+struct Geo;
+template <>
+struct Geo<4> {  // slice = [2 super-tiles][32 lanes][2 words]; row g at +g*32 inside each 256 B
+  static constexpr int kRowStride = 32;
+  __device__ static constexpr int unit_off(int u) { return (u >> 1) * 256 + (u & 1) * 16; }
+  __device__ static constexpr int q(int u, int i) { return (u & 1) * 2 + (i >> 1); }
+  __device__ static constexpr int tp(int u, int i) { return (u >> 1) * 2 + (i & 1); }
+};
+template <>
+struct Geo<2> {  // slice = [4 super-tiles][32 lanes][1 word]; row g at +g*16 inside each 128 B
+  static constexpr int kRowStride = 16;
+  __device__ static constexpr int unit_off(int u) { return u * 128; }
+  __device__ static constexpr int q(int, int i) { return i; }
+  __device__ static constexpr int tp(int u, int) { return u; }
+};
+template <>
+struct Geo<8> {  // slice = [1 super-tile][32 lanes][4 words]; row g at +g*64
+  static constexpr int kRowStride = 64;
+  __device__ static constexpr int unit_off(int u) { return u * 16; }
+  __device__ static constexpr int q(int u, int) { return u; }
+  __device__ static constexpr int tp(int, int i) { return i; }
+};
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+//   M1 = true : exactly one activation row, weights are the mma A operand (two k-sets)
+//   M1 = false: 1..4 activation rows, weights are the mma B operand
+// grid = (row blocks, splits), cluster = (1, splits, 1)
+// ---------------------------------------------------------------------------------------
+template <tg_dtype DT, int IK, bool M1>
+__global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t dyn_base = smem_u32(smem_raw);
+  if (dyn_base > 1024u) __trap();  // layout below assumes the window starts within the first KiB
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int rb = blockIdx.x;                    // row block
+  const int split = blockIdx.y;                 // k split (rank in cluster)
+  const int row0 = rb * kRowsPerCta;
+  const int rows_valid = min(kRowsPerCta, p.w_rows - row0);  // multiple of 8
+  const int tiles_valid = rows_valid >> 3;
+
+  // k range of this CTA, in 128-wide chunks
+  const int chunks_total = (p.k + kChunkK - 1) / kChunkK;
+  const int chunks_per_split = (chunks_total + p.splits - 1) / p.splits;
+  const int chunk_begin = split * chunks_per_split;
+  const int chunk_end = min(chunks_total, chunk_begin + chunks_per_split);
+
+  const int groups_per_chunk = (kChunkK >> p.glog2) > 0 ? (kChunkK >> p.glog2) : 1;
+  const uint32_t stage_bytes = kStageWBytes + 128u * groups_per_chunk;
+  const int n_groups = p.k >> p.glog2;
+
+  // ---- shared memory carve-up (window addresses) ----
+  const uint32_t bar_base = dyn_base;                                   // [kWarps][kStages] mbarriers
+  const uint32_t ring_base = (dyn_base + kWarps * kStages * 8 + 127u) & ~127u;
+  const uint32_t my_ring = ring_base + warp * kStages * stage_bytes;
+  const uint32_t my_bar = bar_base + warp * kStages * 8;
+
+  // ---- producer side: lane 0 of each warp feeds its own ring ----
+  auto issue_chunk = [&](int c, int stage) {
+    // c: absolute chunk index; caller guarantees c < chunk_end
+    const uint32_t bar = my_bar + stage * 8;
+    const uint32_t dst = my_ring + stage * stage_bytes;
+    const int k0 = c * kChunkK;
+    const int kvalid = min(kChunkK, p.k - k0);
+    const uint32_t wbytes = (uint32_t)(kvalid * 4);  // bytes per n-tile for kvalid k: 8 rows * kvalid / 2
+    uint32_t szbytes = 0;
+    int g0 = 0, ng = 0;
+    if (p.sz != nullptr) {
+      g0 = k0 >> p.glog2;
+      ng = min(groups_per_chunk, n_groups - g0);
+      szbytes = (uint32_t)(rows_valid * 4);
+    }
+    mbar_expect_tx(bar, wbytes * tiles_valid + szbytes * ng);
+    const uint8_t* src = p.w + (int64_t)(rb * 4) * p.tile_stride + (int64_t)k0 * 4;
+    for (int t = 0; t < tiles_valid; ++t) {
+      bulk_g2s(dst + t * kTileChunkBytes, src + t * p.tile_stride, wbytes, bar);
+    }
+    for (int g = 0; g < ng; ++g) {
+      bulk_g2s(dst + kStageWBytes + g * 128, p.sz + (int64_t)(g0 + g) * p.w_rows + row0, szbytes, bar);
+    }
+  };
+
+  if (lane == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(my_bar + s * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int s = 0; s < kStages; ++s) {
+      const int c = chunk_begin + warp + s * kWarps;
+      if (c < chunk_end) issue_chunk(c, s);
+    }
+  }
+
+  // ---- pair table: entry e of row L at kTableBase + e*256 + 4L;  warp w builds e in [32w, 32w+32) ----
+  {
+    const int row = min(row0 + lane, p.w_rows - 1);
+    const uint16_t* lrow = p.lut + (int64_t)row * p.lut_stride;
+    const uint4 t0 = *reinterpret_cast<const uint4*>(lrow);
+    const uint4 t1 = *reinterpret_cast<const uint4*>(lrow + 8);
+    const uint32_t tp_[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+    const uint32_t thi = *reinterpret_cast<const uint32_t*>(lrow + 2 * warp);  // (T[2w], T[2w+1])
+    const uint32_t dst = kTableBase + (uint32_t)(warp * 32) * 256u + 4u * lane;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int lo = 0; lo < 16; ++lo) {
+        const uint32_t sel = (h ? 0x7600u : 0x5400u) | ((lo & 1) ? 0x32u : 0x10u);
+        sts32(dst + (uint32_t)(h * 16 + lo) * 256u, prmt(tp_[lo >> 1], thi, sel));
+      }
+    }
+  }
+
+  // ---- activations, permuted so that (x[16t+i], x[16t+i+8]) are adjacent:
+  //      xp[16t + 2i] = x[16t + i], xp[16t + 2i + 1] = x[16t + i + 8], i = 0..7
+  //      linear byte offset o of row r lives at kXBase + ((r*x_row_bytes + o) / 128) * 256 + (o % 128)
+  {
+    const int items_per_row = p.k >> 2;  // one item = 4 k values of one tile = 8 output bytes
+    for (int r = 0; r < p.m; ++r) {
+      const uint32_t* xr = reinterpret_cast<const uint32_t*>(p.x + (int64_t)r * p.k);
+      for (int it = threadIdx.x; it < items_per_row; it += kThreads) {
+        const int t = it >> 2, pp = it & 3;
+        const uint32_t x1 = xr[t * 8 + pp];      // x[16t + 2pp], x[16t + 2pp + 1]
+        const uint32_t x2 = xr[t * 8 + 4 + pp];  // x[16t + 8 + 2pp], x[16t + 9 + 2pp]
+        const uint32_t o = (uint32_t)r * p.x_row_bytes + (uint32_t)it * 8u;
+        sts64(kXBase + (o >> 7) * 256u + (o & 127u), prmt(x1, x2, 0x5410u), prmt(x1, x2, 0x7632u));
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- main loop ----
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};  // second, independent accumulation chain
+  const uint32_t lanebase = kTableBase | (uint32_t)(lane * 4);
+  const int g_ = lane >> 2, q_ = lane & 3;
+  // lanes that carry activations in the block-structured operand
+  const bool set1 = (g_ == q_);          // lanes 0, 5, 10, 15
+  const bool set2 = (g_ == q_ + 4);      // lanes 16, 21, 26, 31
+  const uint32_t x_active = (set1 || set2) ? 1u : 0u;
+  // M1: set1 lanes read tile t0, set2 lanes tile t0+1 (+32 B).  !M1: set1 rows {0,2}, set2 rows {1,3}
+  uint32_t x_lane_off;
+  if constexpr (M1) {
+    x_lane_off = set2 ? 32u : 0u;
+  } else {
+    const uint32_t o = set2 ? (uint32_t)p.x_row_bytes : 0u;
+    x_lane_off = (o >> 7) * 256u + (o & 127u);
+  }
+  // second pair of rows (mi + 2) for the !M1 kernel
+  const uint32_t x_row2 = ((2u * (uint32_t)p.x_row_bytes) >> 7) * 256u;  // x_row_bytes % 128 == 0
+  const bool has_row01 = M1 ? true : (set1 || p.m > 1);
+  const bool has_row23 = M1 ? false : (set1 ? p.m > 2 : p.m > 3);
+  const uint32_t xa01 = (x_active && has_row01) ? 1u : 0u;
+  const uint32_t xa23 = (x_active && has_row23) ? 1u : 0u;
+
+  const uint32_t w_lane_off = (uint32_t)(lane >> 3) * kTileChunkBytes + (uint32_t)(lane & 7) * Geo<IK>::kRowStride;
+  const uint32_t sz_lane_off = kStageWBytes + (uint32_t)lane * 4u;
+  const bool is_mx4 = (p.sz == nullptr);
+  const uint8_t* my_exps = is_mx4 ? p.exps + (int64_t)min(row0 + lane, p.w_rows - 1) * n_groups : nullptr;
+
+  uint32_t xr0[4] = {0u, 0u, 0u, 0u}, xr1[4] = {0u, 0u, 0u, 0u};  // x fragments (stay zero on inactive lanes)
+  uint32_t xs0[4] = {0u, 0u, 0u, 0u}, xs1[4] = {0u, 0u, 0u, 0u};  // rows mi+2 (!M1)
+
+  int it = 0;
+  for (int c = chunk_begin + warp; c < chunk_end; c += kWarps, ++it) {
+    const int stage = it % kStages;
+    const uint32_t parity = (uint32_t)(it / kStages) & 1u;
+    const uint32_t sbase = my_ring + stage * stage_bytes;
+    const int kvalid = min(kChunkK, p.k - c * kChunkK);
+
+    // group scale / zero for the four tile pairs (32 k each) of this chunk
+    uint32_t s2[4], z2[4];
+    if (is_mx4) {
+      const int g0 = (c * kChunkK) >> p.glog2;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int gi = min(g0 + ((t * 32) >> p.glog2), n_groups - 1);
+        const uint32_t s = e8m0_to_dt<DT>((uint32_t)my_exps[gi]);
+        s2[t] = s | (s << 16);
+        z2[t] = 0x80008000u;  // -0: fma(v, s, -0) == v * s including the sign of zero
+      }
+    }
+    mbar_wait(my_bar + stage * 8, parity);
+    if (!is_mx4) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t v = lds32(sbase + sz_lane_off + (uint32_t)((t * 32) >> p.glog2) * 128u);
+        s2[t] = prmt(v, v, 0x1010u);
+        z2[t] = prmt(v, v, 0x3232u);
+      }
+    }
+
+    // x base for this chunk: tile t0 = 8c + 2tp ; byte offset 32*t0 -> piece (t0/4), within (t0%4)*32
+    const uint32_t xc = kXBase + (uint32_t)c * 512u + x_lane_off;
+
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (u * 32 < kvalid) {  // warp-uniform tail guard (k % 128 != 0)
+        const uint4 wv = lds128(sbase + w_lane_off + Geo<IK>::unit_off(u));
+        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int q = Geo<IK>::q(u, i);
+          const int tp = Geo<IK>::tp(u, i);
+          const uint32_t w = ww[i];
+          // byte0: tile 2tp (k0, k0+8)   byte2: tile 2tp (k0+1, k0+9)
+          // byte1: tile 2tp+1 (k0, k0+8) byte3: tile 2tp+1 (k0+1, k0+9)
+          uint32_t p0 = lds32(prmt(w, lanebase, 0x7604u));
+          uint32_t p1 = lds32(prmt(w, lanebase, 0x7614u));
+          uint32_t p2 = lds32(prmt(w, lanebase, 0x7624u));
+          uint32_t p3 = lds32(prmt(w, lanebase, 0x7634u));
+          p0 = fma2<DT>(p0, s2[tp], z2[tp]);
+          p1 = fma2<DT>(p1, s2[tp], z2[tp]);
+          p2 = fma2<DT>(p2, s2[tp], z2[tp]);
+          p3 = fma2<DT>(p3, s2[tp], z2[tp]);
+          // x for tile 2tp, slot q: bytes (tp/2)*256 + (tp%2)*64 + 8q of this chunk's x
+          const uint32_t xo = xc + (uint32_t)((tp >> 1) * 256 + (tp & 1) * 64 + q * 8);
+          if constexpr (M1) {
+            lds64_if(xr0[i], xr1[i], xo, x_active);
+            // A = weights: a0/a2 = k-set 1 (tile 2tp), a1/a3 = k-set 2 (tile 2tp+1)
+            mma16816<DT>((i & 1) ? accb : acc, p0, p1, p2, p3, xr0[i], xr1[i]);
+          } else {
+            float(&accA)[4] = (i & 1) ? accb : acc;
+            lds64_if(xr0[i], xr1[i], xo, xa01);
+            lds64_if(xs0[i], xs1[i], xo + x_row2, xa23);
+            // tile 2tp: B = (byte0, byte2); A = x (a0,a2 rows mi, a1,a3 rows mi+2)
+            mma16816<DT>(accA, xr0[i], xs0[i], xr1[i], xs1[i], p0, p2);
+            uint32_t y0 = 0u, y1 = 0u, v0 = 0u, v1 = 0u;
+            lds64_if(y0, y1, xo + 32u, xa01);
+            lds64_if(v0, v1, xo + 32u + x_row2, xa23);
+            mma16816<DT>(accA, y0, v0, y1, v1, p1, p3);
+          }
+        }
+      }
+    }
+
+    // refill this stage with the chunk kStages rounds ahead
+    __syncwarp();
+    const int cn = c + kStages * kWarps;
+    if (lane == 0 && cn < chunk_end) issue_chunk(cn, stage);
+  }
+
+  // ---- epilogue: cross-warp (and cross-CTA) reduction, one rounding, store ----
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] += accb[i];
+  // red[warp][j][row] fp32 at kRedBase
+  {
+    const uint32_t rbase = kRedBase + (uint32_t)warp * 512u;
+    if constexpr (M1) {
+      // valid: lanes q_<2: acc[0],acc[1] = rows 4g+2q_, 4g+2q_+1 (k-set 1); lanes q_>=2: acc[2],acc[3] = rows
+      // 4g+2(q_-2), +1 (k-set 2)
+      const int j = q_ >> 1;
+      const int r = 4 * g_ + 2 * (q_ & 1);
+      const float v0 = j ? acc[2] : acc[0];
+      const float v1 = j ? acc[3] : acc[1];
+      sts32(rbase + (uint32_t)(j * 32 + r) * 4u, __float_as_uint(v0));
+      sts32(rbase + (uint32_t)(j * 32 + r + 1) * 4u, __float_as_uint(v1));
+      // slots j = 2, 3 unused
+    } else {
+      // acc[0],acc[1] = C[g_][2q_, 2q_+1]: mi = g_/4, rows 4*(2q_)+g_%4 and 4*(2q_+1)+g_%4; acc[2],acc[3]: mi + 2
+      const int mi = g_ >> 2, qq = g_ & 3;
+      sts32(rbase + (uint32_t)(mi * 32 + 8 * q_ + qq) * 4u, __float_as_uint(acc[0]));
+      sts32(rbase + (uint32_t)(mi * 32 + 8 * q_ + 4 + qq) * 4u, __float_as_uint(acc[1]));
+      sts32(rbase + (uint32_t)((mi + 2) * 32 + 8 * q_ + qq) * 4u, __float_as_uint(acc[2]));
+      sts32(rbase + (uint32_t)((mi + 2) * 32 + 8 * q_ + 4 + qq) * 4u, __float_as_uint(acc[3]));
+    }
+  }
+  __syncthreads();
+
+  // CTA-level sums: thread (j, row) -> sum over warps, written back to red[0][j][row]
+  const int nj = M1 ? 1 : p.m;
+  float total = 0.f;
+  const int tj = threadIdx.x >> 5, trow = threadIdx.x & 31;
+  if (threadIdx.x < 128) {
+    if constexpr (M1) {
+      if (tj == 0) {
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          total += __uint_as_float(lds32(kRedBase + (uint32_t)w * 512u + (uint32_t)trow * 4u));
+          total += __uint_as_float(lds32(kRedBase + (uint32_t)w * 512u + (uint32_t)(32 + trow) * 4u));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w)
+        total += __uint_as_float(lds32(kRedBase + (uint32_t)w * 512u + (uint32_t)(tj * 32 + trow) * 4u));
+    }
+  }
+
+  if (p.splits == 1) {
+    if (threadIdx.x < 128 && tj < nj && trow < rows_valid)
+      p.y[(int64_t)tj * p.y_stride + row0 + trow] = f32_to_dt<DT>(total);
+    return;
+  }
+
+  // split-k: every CTA of the cluster publishes its 32 x nj partials; rank 0 adds them in rank order
+  cg::cluster_group cluster = cg::this_cluster();
+  __syncthreads();  // everyone is done reading red[] of all warps
+  float* part = reinterpret_cast<float*>(smem_raw + (kRedBase - dyn_base));
+  if (threadIdx.x < 128) part[tj * 32 + trow] = total;
+  cluster.sync();
+  if (cluster.block_rank() == 0 && threadIdx.x < 128 && tj < nj) {
+    float sum = total;
+    for (int r = 1; r < p.splits; ++r) {
+      const float* remote = cluster.map_shared_rank(part, r);
+      sum += remote[tj * 32 + trow];
+    }
+    if (trow < rows_valid) p.y[(int64_t)tj * p.y_stride + row0 + trow] = f32_to_dt<DT>(sum);
+  }
+  cluster.sync();  // keep remote shared memory alive until rank 0 has read it
+}
+
+template <tg_dtype DT, int IK, bool M1>
+int launch_one(const Params& p, int row_blocks, cudaStream_t st) {
+  auto kern = gemv_w4_b_kernel<DT, IK, M1>;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBytes) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%u) failed: %s", kDynSmemBytes, cudaGetErrorString(cudaGetLastError()));
+      return TG_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)row_blocks, (unsigned)p.splits, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kDynSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 1;
+  attrs[0].val.clusterDim.y = (unsigned)p.splits;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) {
+    set_error("gemv_w4_b launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return TG_ERR_CUDA;
+  }
+  count_launch();
+  return TG_OK;
+}
+
+template <tg_dtype DT, int IK>
+int launch_m(Params p, int row_blocks, int64_t rows_x, const uint16_t* x, uint16_t* y, cudaStream_t st) {
+  // activation rows are processed in passes of up to 4 (bounded by the staging area)
+  const int cap = kMaxXBytes / p.x_row_bytes;
+  if (cap < 1) {
+    set_error("k = %d is too large for the shared-memory activation stage (max %d)", p.k, kMaxXBytes / 2);
+    return TG_ERR_UNSUPPORTED;
+  }
+  const int per_pass = cap < 4 ? cap : 4;
+  for (int64_t r0 = 0; r0 < rows_x; r0 += per_pass) {
+    p.m = (int)((rows_x - r0) < per_pass ? (rows_x - r0) : per_pass);
+    p.x = x + r0 * p.k;
+    p.y = y + r0 * p.y_stride;
+    int rc = (p.m == 1) ? launch_one<DT, IK, true>(p, row_blocks, st) : launch_one<DT, IK, false>(p, row_blocks, st);
+    if (rc != TG_OK) return rc;
+  }
+  return TG_OK;
+}
+
+template <tg_dtype DT>
+int launch_ik(const Params& p, int ik, int row_blocks, int64_t rows_x, const uint16_t* x, uint16_t* y,
+              cudaStream_t st) {
+  switch (ik) {
+    case 2: return launch_m<DT, 2>(p, row_blocks, rows_x, x, y, st);
+    case 4: return launch_m<DT, 4>(p, row_blocks, rows_x, x, y, st);
+    case 8: return launch_m<DT, 8>(p, row_blocks, rows_x, x, y, st);
+  }
+  set_error("B-layout int4 innerKTiles must be 2, 4 or 8 (got %d)", ik);
+  return TG_ERR_INVALID_ARGUMENT;
+}
+
+}  // namespace
+
+int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
+                        const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
+                        tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st) {
+  Params p{};
+  p.w = reinterpret_cast<const uint8_t*>(w);
+  p.sz = (fmt == TG_W4_MX4) ? nullptr : reinterpret_cast<const uint32_t*>(sz);
+  p.exps = (fmt == TG_W4_MX4) ? exps : nullptr;
+  p.w_rows = (int)w_rows;
+  p.k = (int)k;
+  p.glog2 = group == 32 ? 5 : group == 64 ? 6 : group == 128 ? 7 : 8;
+  p.tile_stride = 4 * k;
+  p.y_stride = w_rows;
+  p.x_row_bytes = (int)((2 * k + 127) / 128 * 128);
+
+  if (fmt == TG_W4_ANY4_GLOBAL || fmt == TG_W4_ANY4_ROWWISE) {
+    p.lut = reinterpret_cast<const uint16_t*>(lut);
+    p.lut_stride = (fmt == TG_W4_ANY4_ROWWISE) ? 16 : 0;
+  } else {
+    p.lut = const_lut;  // int4 / mx4: constant table, same for every row
+    p.lut_stride = 0;
+  }
+
+  const int row_blocks = (int)div_up(w_rows, kRowsPerCta);
+  // split k across a cluster when the row blocks alone cannot fill the machine
+  const int chunks = (int)div_up(k, kChunkK);
+  int splits = 1;
+  while (splits < 8 && row_blocks * splits * 2 <= 148 && chunks / (splits * 2) >= 8) splits *= 2;
+  p.splits = splits;
+
+  if (dt == TG_BF16)
+    return launch_ik<TG_BF16>(p, ik, row_blocks, rows_x, (const uint16_t*)x, (uint16_t*)y, st);
+  return launch_ik<TG_FP16>(p, ik, row_blocks, rows_x, (const uint16_t*)x, (uint16_t*)y, st);
+}
+
+}  // namespace tg

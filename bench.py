@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py - the hot-path benchmark (BASELINE.json configs[1]):
+tinygemm any4-bf16 GEMV, m = 1, n = k = 4096 (headline) plus 8192 and 11008, g = 128.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one GEMV on each of `copies` distinct synthetic weight sets of the headline shape
+(the copies total > 2.5x the 126 MB L2, so every launch streams its weights from HBM).
+value   = algorithmic GB/s (SURVEY.md 8d byte count) with everything resident in HBM
+e2e     = same metric through the public module API (any4_b200.modules.Any4Linear) with HOST
+          buffers: pinned x -> device, GEMV, y -> host, every call
+N > 1   = the weight rows are sharded across ranks (RowShardedLinear), one NCCL all-reduce on
+          the m x n output per GEMV; value = total algorithmic bytes / max-over-ranks time
+--impl reference times the reference's own CPU path (quantize.py:612-637 dequant + F.linear,
+restated in oracle/cpu_path.py) on the host cores for the same config.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+G = 128
+HEADLINE = 4096
+EXTRA_SHAPES = (8192, 11008)
+METRIC = "any4_gemv_m1_n4096_k4096_g128_algorithmic_GBps"
+
+
+def algorithmic_bytes(n, k, m=1, g=G):
+    """packed weights + scale/zero + per-row LUT + x + y (bf16)"""
+    return n * k // 2 + (k // g) * n * 4 + n * 32 + 2 * m * k + 2 * m * n
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_layer(n, k, seed, device, rows=None):
+    """Synthetic any4 layer (SURVEY.md 8d recipe), generated on the device: packed codes are
+    uniformly random nibbles, so the packed words are drawn directly (equivalent to packing
+    randint(0,16) codes, and 8x less memory than the int32 code matrix)."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    rows = n if rows is None else rows
+    w = torch.randint(-2**31, 2**31 - 1, (rows // 8, k // 64, 32, 2), generator=gen, device=device,
+                      dtype=torch.int64).to(torch.int32)
+    lut = ((torch.rand(rows, 16, generator=gen, device=device) * 15).sort(1).values.bfloat16() - 8)
+    scale = torch.rand(k // G, rows, generator=gen, device=device) * 0.01 + 0.001
+    zero = torch.randn(k // G, rows, generator=gen, device=device) * 0.01
+    sz = torch.stack([scale, zero], dim=2).bfloat16().contiguous()
+    return w, lut, sz
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [v.strip() for v in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def time_gemv_set(call, n_calls_per_step, steps, warmup, dist=None):
+    """W untimed steps, then exactly K timed steps bracketed by barrier + synchronize; CUDA events
+    on the launching (current) stream; returns max-over-ranks milliseconds for the K steps."""
+    for _ in range(warmup):
+        call()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    return ms
+
+
+def cpu_baseline(seconds=12.0):
+    """The reference's CPU path (dense dequant + F.linear) on the host cores, bounded sample."""
+    from oracle import cpu_path
+
+    n = k = HEADLINE
+    gen = torch.Generator().manual_seed(0)
+    assign = torch.randint(0, 16, (n, k), generator=gen, dtype=torch.int32)
+    any4 = (torch.rand(n, 16, generator=gen) * 15).sort(1).values.bfloat16()
+    sz = torch.stack([torch.rand(k // G, n, generator=gen) * 0.01 + 0.001,
+                      torch.randn(k // G, n, generator=gen) * 0.01], dim=2).bfloat16()
+    x = torch.randn(1, k, generator=gen).bfloat16()
+    for _ in range(2):
+        cpu_path.any4_linear_forward(x, assign, any4, sz, G, True)
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        cpu_path.any4_linear_forward(x, assign, any4, sz, G, True)
+        reps += 1
+        if time.perf_counter() - t0 > seconds or reps >= 200:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": algorithmic_bytes(n, k) / dt / 1e9, "unit": "GB/s", "cores": torch.get_num_threads(),
+            "kind": "port", "ms_per_forward": dt * 1e3,
+            "sample": f"{reps} forwards of one 4096x4096 g=128 m=1 any4 Linear (dense dequant + F.linear, bf16)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_path
+
+    n = k = HEADLINE
+    per_step = 2  # bounded sample: 2 forwards per step (ours: `copies` GEMVs per step)
+    gen = torch.Generator().manual_seed(0)
+    assign = torch.randint(0, 16, (n, k), generator=gen, dtype=torch.int32)
+    any4 = (torch.rand(n, 16, generator=gen) * 15).sort(1).values.bfloat16()
+    sz = torch.stack([torch.rand(k // G, n, generator=gen) * 0.01 + 0.001,
+                      torch.randn(k // G, n, generator=gen) * 0.01], dim=2).bfloat16()
+    x = torch.randn(1, k, generator=gen).bfloat16()
+
+    def step():
+        for _ in range(per_step):
+            cpu_path.any4_linear_forward(x, assign, any4, sz, G, True)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = algorithmic_bytes(n, k) * per_step * args.steps / dt / 1e9
+    cores = torch.get_num_threads()
+    sample = f"{per_step} forwards/step of the 4096x4096 g=128 m=1 any4 Linear on CPU (dense dequant + F.linear)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "any4-bf16 GEMV m=1 n=k=4096 g=128 per-row LUT", "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+
+    from any4_b200 import _native
+    from any4_b200.modules import Any4Linear, RowShardedLinear
+
+    lib = _native.capi()
+    peak, peak_src = measured_peak()
+
+    def build_layers(n, k, copies):
+        layers = []
+        for i in range(copies):
+            lin = Any4Linear(k, n, bias=False, device=dev, dtype=torch.bfloat16, group_size=G)
+            w, lut, sz = synth_layer(n, k, 1234 + i, dev)
+            lin.weight.data, lin.lut.data, lin.scales_and_zeros.data = w, lut, sz
+            lin.weight_reshaped = True
+            layers.append(RowShardedLinear(lin, rank, world) if world > 1 else lin)
+        return layers
+
+    def bench_shape(n, k, steps, warmup, with_e2e):
+        nbytes = algorithmic_bytes(n, k)
+        copies = max(3, int(2.6 * 126e6 / nbytes) + 1)
+        layers = build_layers(n, k, copies)
+        x = torch.randn(1, k, device=dev).bfloat16()
+        ys = [None]
+
+        def step():
+            for lin in layers:
+                ys[0] = lin(x)
+
+        lib.tg_reset_launch_count()
+        ms = time_gemv_set(step, copies, steps, warmup, dist)
+        launches = int(lib.tg_launch_count()) * steps // (steps + warmup)
+        out = {"n": n, "k": k, "copies": copies, "ms": ms, "launches": launches,
+               "us_per_gemv": ms * 1e3 / (steps * copies),
+               "gbps": nbytes * copies * steps / (ms * 1e-3) / 1e9}
+        if with_e2e:
+            xh = torch.randn(1, k).bfloat16().pin_memory()
+            yh = torch.empty(1, n, dtype=torch.bfloat16).pin_memory()
+            xd = torch.empty(1, k, device=dev, dtype=torch.bfloat16)
+
+            def step_e2e():
+                for lin in layers:
+                    xd.copy_(xh, non_blocking=True)
+                    yh.copy_(lin(xd), non_blocking=True)
+                torch.cuda.synchronize()
+
+            ms2 = time_gemv_set(step_e2e, copies, steps, warmup, dist)
+            out["e2e_gbps"] = nbytes * copies * steps / (ms2 * 1e-3) / 1e9
+            out["h2d"] = copies * k * 2
+            out["d2h"] = copies * n * 2
+        del layers
+        torch.cuda.empty_cache()
+        return out
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    head = bench_shape(HEADLINE, HEADLINE, args.steps, args.warmup, True)
+    extra = [bench_shape(s, s, max(3, args.steps // 2), args.warmup, False) for s in EXTRA_SHAPES]
+    clocks = sampler.stop() if sampler else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline()
+
+    if rank == 0:
+        nbytes = algorithmic_bytes(HEADLINE, HEADLINE)
+        per_rank_bytes = nbytes / world  # each rank streams 1/world of the rows (x replicated, negligible)
+        us = head["us_per_gemv"]
+        achieved = per_rank_bytes / (us * 1e-6) / 1e9
+        line = {
+            "metric": METRIC, "value": head["gbps"], "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms"] / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {
+                "workload": "any4-bf16 GEMV m=1 n=k=4096 g=128 per-row LUT (BASELINE configs[1])",
+                "gemvs_per_step": head["copies"],
+                "l2_policy": f"inputs larger than L2: {head['copies']} distinct weight sets = "
+                             f"{head['copies'] * nbytes / 1e6:.0f} MB rotated every step",
+                "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world} + NCCL all-reduce on y",
+                "other_shapes": {f"{e['n']}x{e['k']}": {"GBps": round(e["gbps"], 1), "us_per_gemv": round(e["us_per_gemv"], 3),
+                                                         "frac_of_peak": round(e["gbps"] / world / peak, 4)} for e in extra},
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src + " (of measured)",
+                         "kernel": "gemv_w4_b_kernel<bf16, ik=4, m=1>", "us_per_launch": us,
+                         "algorithmic_bytes_per_launch": per_rank_bytes},
+            "e2e": {"value": head["e2e_gbps"], "unit": "GB/s", "h2d_bytes_per_step": head["h2d"],
+                    "d2h_bytes_per_step": head["d2h"]},
+            "gpu_launches": head["launches"],
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

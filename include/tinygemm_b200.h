@@ -1,0 +1,170 @@
+/*
+ * tinygemm_b200 - C ABI of the B200-native (sm_100a) tinygemm replacement.
+ *
+ * This header is the drop-in boundary of the repo: plain device pointers, sizes and a
+ * cudaStream_t (passed as void*) - no torch types.  Every entry point below replaces
+ * one operator of the reference's torch extension (reference = facebookresearch/any4,
+ * directory tinygemm_lib/; schemas at TinyGemm.cpp:19-121, declarations with the layout
+ * comments at TinyGemm.h:19-216).  The torch custom-op layer that re-creates
+ * `torch.ops.tinygemm.*` on top of this ABI lives in any4_b200/csrc/torch_ops.cpp.
+ *
+ * Conventions
+ *   - all pointers are device pointers on the current CUDA device unless stated otherwise
+ *   - all tensors are dense / contiguous in the layouts written next to each function
+ *   - every call is asynchronous on `stream` and never synchronises the device
+ *   - return value: TG_OK (0) or a negative TG_ERR_* code; tg_last_error() returns a
+ *     human-readable message for the last failure on the calling thread
+ *   - there is NO CPU fallback: a call on a machine without a usable sm_100 device
+ *     fails with TG_ERR_CUDA
+ */
+#ifndef TINYGEMM_B200_H
+#define TINYGEMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_OK 0
+#define TG_ERR_INVALID_ARGUMENT (-1) /* shape / enum / alignment check failed (reference: TORCH_CHECK) */
+#define TG_ERR_CUDA (-2)             /* CUDA runtime error at launch */
+#define TG_ERR_UNSUPPORTED (-3)      /* combination the reference rejects as well */
+
+/* activation / output element type ("f16" in the reference op names) */
+typedef enum { TG_BF16 = 0, TG_FP16 = 1 } tg_dtype;
+
+/* 4-bit weight formats; reference: Int4_QType, TinyGemmUtils.cuh:21-32 */
+typedef enum {
+  TG_W4_INT4 = 0,         /* uniform int4: w = (code - 8) * scale + zero                */
+  TG_W4_ANY4_GLOBAL = 1,  /* one 16-entry LUT for the matrix (nf4/fp4/af4 run this way)  */
+  TG_W4_ANY4_ROWWISE = 2, /* one 16-entry LUT per (padded) weight row                    */
+  TG_W4_MX4 = 3           /* fp4 e2m1 codes + one e8m0 exponent per (row, group)         */
+} tg_w4_format;
+
+/* which mma operand the packed weight was laid out for (reference: `weightOnRight`) */
+typedef enum {
+  TG_WEIGHT_B = 1, /* weightOnRight = true : y = x W^T, W in "B" layout (8-row tiles)  */
+  TG_WEIGHT_A = 0  /* weightOnRight = false: y = (W x^T)^T, W in "A" layout (16-row tiles) */
+} tg_weight_side;
+
+const char* tg_last_error(void);
+/* library / build identification, e.g. "tinygemm_b200 0.1 sm_100a" */
+const char* tg_version(void);
+/* number of kernels launched by this library on the calling thread since the last reset
+ * (used by bench.py for its `gpu_launches` claim) */
+uint64_t tg_launch_count(void);
+void tg_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Layout conversion ("convert_matrix_*" ops).  Bit-exact with the reference kernels.
+ * Lane geometry: lane t of a warp, g = t / 4, q = t % 4, k0 = kTile * 16 + 2 * q.
+ * ---------------------------------------------------------------------------------- */
+
+/* [m][k] 16-bit -> [ceil(m/16)][ceil(k/16)][32][8], zero padded.
+ * replaces convert_matrix_to_m16n8k16_A_layout (TinyGemmConvertA.cu:150-223; kernel :19-141) */
+int tg_convert_to_A(const void* in, void* out, int64_t m, int64_t k, void* stream);
+
+/* inverse of the above. replaces convert_matrix_from_m16n8k16_A_layout
+ * (TinyGemmConvertA.cu:554-626; kernel :442-546) */
+int tg_convert_from_A(const void* in, void* out, int64_t m, int64_t k, void* stream);
+
+/* [n][k] 16-bit -> [ceil(n/8)][ceil(k/(ik*16))][32][ik*4], ik in {1,2}.
+ * replaces convert_matrix_to_m16n8k16_B_layout (TinyGemmConvertB.cu:76-133; kernel :20-66) */
+int tg_convert_to_B(const void* in, void* out, int64_t n, int64_t k, int inner_k_tiles, void* stream);
+
+/* inverse. replaces convert_matrix_from_m16n8k16_B_layout (TinyGemmConvertB.cu:186-249; kernel :136-176) */
+int tg_convert_from_B(const void* in, void* out, int64_t n, int64_t k, int inner_k_tiles, void* stream);
+
+/* [m][k] int32 codes (0..15) -> [ceil(m/16)][ceil(k/(ik*16))][32][ik] int32, ik in {1,2,4}.
+ * replaces convert_matrix_to_m16n8k16_Aint4_layout (TinyGemmConvertA.cu:289-333; kernel :226-285) */
+int tg_convert_to_Aint4(const int32_t* in, int32_t* out, int64_t m, int64_t k, int inner_k_tiles, void* stream);
+
+/* [m][k] int32 codes (0..255) -> [ceil(m/16)][ceil(ceil(k/16)/ik)][32][2*ik] int32, ik in {1,2}.
+ * replaces convert_matrix_to_m16n8k16_Aint8_layout (TinyGemmConvertA.cu:400-440; kernel :340-396) */
+int tg_convert_to_Aint8(const int32_t* in, int32_t* out, int64_t m, int64_t k, int inner_k_tiles, void* stream);
+
+/* [n][k] int32 codes (0..15) -> [ceil(n/8)][k/(ik*16)][32][ik/2] int32, ik in {2,4,8}, k % (ik*16) == 0.
+ * replaces convert_matrix_to_m16n8k16_Bint4_layout (TinyGemmConvertB.cu:312-364; kernel :252-308) */
+int tg_convert_to_Bint4(const int32_t* in, int32_t* out, int64_t n, int64_t k, int inner_k_tiles, void* stream);
+
+/* [n][k] int32 codes (0..255) -> [ceil(n/8)][k/(ik*16)][32][ik] int32, ik in {1,2,4}, k % (ik*16) == 0.
+ * replaces convert_matrix_to_m16n8k16_Bint8_layout (TinyGemmConvertB.cu:415-464; kernel :367-410) */
+int tg_convert_to_Bint8(const int32_t* in, int32_t* out, int64_t n, int64_t k, int inner_k_tiles, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Weight-only small-batch GEMM, row-major activations and output
+ * ("tinygemm_y_f16RM_x_f16RM_w_*TC" ops).
+ *
+ *   x        [rows_x][k]            dtype           (any rows_x >= 1; tuned for <= 16)
+ *   y        [rows_x][w_rows]       dtype           (w_rows = padded weight rows, see below)
+ *   w        packed weight in the A- or B- tensor-core layout produced by tg_convert_to_*
+ *   w_rows   PADDED number of weight rows: 8 * nTiles (TG_WEIGHT_B) or 16 * mTiles (TG_WEIGHT_A)
+ *   k        reduction length, k % 32 == 0 (reference: TinyGemmImpl.cuh:372-376)
+ *
+ * Numerics contract (reference: Dequantization.cuh, MatrixLayoutB.cuh:1005-1088,
+ * FloatDefs.cuh:87-119): every weight is v = LUT[code] in `dtype`, then
+ * fma.rn(v, scale, zero) with ONE rounding to `dtype` (mx4: v * 2^(e-127), e==255 -> NaN);
+ * products with x are exact and accumulated in fp32; one round-to-nearest-even at the end.
+ * ---------------------------------------------------------------------------------- */
+
+/* int4 / any4 / mx4.  replaces tinygemm_y_f16RM_x_f16RM_w_{int4,any4,mx4}TC
+ * (TinyGemm_int4.cu:294-548 dispatch, :550-794 public ops).
+ *   scales_zeros  [k/group][w_rows][2] dtype       (int4 / any4; ignored for mx4)
+ *   lut           [16] (global) or [w_rows][16] dtype (any4 only)
+ *   exponents     [w_rows][k/group] uint8 e8m0     (mx4 only; dtype must be TG_BF16)
+ *   group         32, 64, 128 or 256
+ *   inner_k_tiles B layout: 2, 4, 8;  A layout: 1, 2, 4  */
+int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
+                  const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
+                  int inner_k_tiles, tg_w4_format format, tg_weight_side side, tg_dtype dtype, void* stream);
+
+/* int8.  replaces tinygemm_y_f16RM_x_f16RM_w_int8TC (TinyGemm_int8.cu:215-399, :430-457).
+ *   inner_k_tiles B layout: 1, 2, 4;  A layout: 1, 2 */
+int tg_gemm_w8_rm(void* y, const void* x, const int32_t* w, const void* scales_zeros, int64_t rows_x,
+                  int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_weight_side side,
+                  tg_dtype dtype, void* stream);
+
+/* 16-bit weights.  replaces tinygemm_y_f16RM_x_f16RM_w_f16TC (TinyGemm_bf16.cu:163-293, :312-327).
+ *   w in the 16-bit A layout (ik 1) or B layout (ik 1, 2); k_padded = 16 * kTiles of the weight */
+int tg_gemm_w16_rm(void* y, const void* x, const void* w, int64_t rows_x, int64_t w_rows, int64_t k,
+                   int inner_k_tiles, tg_weight_side side, tg_dtype dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Tensor-core-layout activations and output ("tinygemm_y_f16TC_x_f16TC_w_*TC" ops,
+ * TinyGemm_int4.cu:28-292, TinyGemm_int8.cu:22-213, TinyGemm_bf16.cu:35-150).
+ *
+ * TG_WEIGHT_B: x is in the 16-bit A layout [mT][kT][32][8]; y is written in the 16-bit A
+ *              layout [mT][ceil(nT/2)][32][8] (n plays the role of k).
+ * TG_WEIGHT_A: x is in the 16-bit B layout [nT][ceil(kT/x_ik)][32][x_ik*4]; y is written in
+ *              the B layout [nT][ceil(mT/x_ik)][32][x_ik*4] (weight rows play the role of k).
+ * rows_x here is the PADDED activation row count (16*mT or 8*nT).  `workspace` must hold
+ * tg_gemm_tc_workspace_bytes(rows_x, w_rows, k) bytes of device memory; it is used for the
+ * row-major staging of x and y and may be reused as soon as the call's work on `stream`
+ * has completed.
+ * ---------------------------------------------------------------------------------- */
+size_t tg_gemm_tc_workspace_bytes(int64_t rows_x, int64_t w_rows, int64_t k);
+
+int tg_gemm_w4_tc(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
+                  const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
+                  int inner_k_tiles, int x_inner_k_tiles, tg_w4_format format, tg_weight_side side,
+                  tg_dtype dtype, void* workspace, void* stream);
+
+int tg_gemm_w8_tc(void* y, const void* x, const int32_t* w, const void* scales_zeros, int64_t rows_x,
+                  int64_t w_rows, int64_t k, int group, int inner_k_tiles, int x_inner_k_tiles,
+                  tg_weight_side side, tg_dtype dtype, void* workspace, void* stream);
+
+int tg_gemm_w16_tc(void* y, const void* x, const void* w, int64_t rows_x, int64_t w_rows, int64_t k,
+                   int inner_k_tiles, int x_inner_k_tiles, tg_weight_side side, tg_dtype dtype,
+                   void* workspace, void* stream);
+
+/* debug op: 8 x int4 -> 8 x bf16 per int32 word, value = code - 8, element order
+ * v0 v1 ... v7 of the packed word.  replaces tinygemm_dequant_int4 (TinyGemmDequantize.cu:19-58).
+ *   in [n_words] int32 -> out [n_words][8] bf16 */
+int tg_dequant_int4(const int32_t* in, void* out, int64_t n_words, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINYGEMM_B200_H */

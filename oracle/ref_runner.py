@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Run the UNMODIFIED reference tinygemm extension (oracle/_ref/tinygemm.so) on the GPU.
+TEST INFRASTRUCTURE ONLY.  Must be its own process: the reference registers the same
+`torch.ops.tinygemm` namespace as this repo's library.
+
+  python oracle/ref_runner.py golden <out.npz>      evaluate every parity case (oracle/cases.py)
+  python oracle/ref_runner.py bench <n> <k> <iters> time the reference any4 GEMV (rotating copies)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+SO = os.path.join(HERE, "_ref", "tinygemm.so")
+
+
+def load_reference():
+    if not os.path.exists(SO):
+        raise SystemExit(f"{SO} missing: build it in the build container with `python oracle/build_ref.py`")
+    torch.ops.load_library(SO)
+
+
+def golden(out_path):
+    from oracle import cases as C
+
+    load_reference()
+    out = {}
+    for c in C.all_cases():
+        inp = C.make_inputs(c)
+        try:
+            res = C.run_ops(c, inp, "cuda:0")
+        except RuntimeError as e:
+            print(f"[ref] {C.case_id(c)} rejected by the reference: {str(e).splitlines()[0][:120]}")
+            continue
+        for key, t in res.items():
+            name = f"{C.case_id(c)}/{key}"
+            if t.dtype in (torch.bfloat16, torch.float16):
+                out[name] = t.contiguous().view(torch.int16).numpy().view(np.uint16)
+            else:
+                out[name] = t.numpy()
+    torch.cuda.synchronize()
+    np.savez_compressed(out_path, **out)
+    print(f"[ref] wrote {out_path}: {len(out)} arrays")
+
+
+def bench(n, k, iters):
+    load_reference()
+    g = 128
+    dev = torch.device("cuda:0")
+    nbytes = n * k // 2 + (k // g) * n * 4 + n * 32 + 2 * k + 2 * n
+    copies = max(3, int(2.6 * 126e6 / nbytes) + 1)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    layers = []
+    for _ in range(copies):
+        w = torch.randint(-2**31, 2**31 - 1, (n // 8, k // 64, 32, 2), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+        lut = ((torch.rand(n, 16, generator=gen, device=dev) * 15).sort(1).values.bfloat16() - 8)
+        sz = torch.stack([torch.rand(k // g, n, generator=gen, device=dev) * 0.01 + 0.001,
+                          torch.randn(k // g, n, generator=gen, device=dev) * 0.01], dim=2).bfloat16().contiguous()
+        layers.append((w, lut, sz))
+    x = torch.randn(1, k, device=dev).bfloat16()
+    op = torch.ops.tinygemm.tinygemm_y_f16RM_x_f16RM_w_any4TC
+    for _ in range(3):
+        for w, lut, sz in layers:
+            op(x, w, g, sz, lut, True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        for w, lut, sz in layers:
+            op(x, w, g, sz, lut, True)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (iters * copies)
+    print(json.dumps({"impl": "reference tinygemm (mma.sync, recompiled for sm_100a)", "n": n, "k": k,
+                      "us_per_gemv": us, "GBps": nbytes / us / 1e3, "copies": copies}))
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "golden":
+        golden(sys.argv[2])
+    elif sys.argv[1] == "bench":
+        bench(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))

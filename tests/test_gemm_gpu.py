@@ -1,0 +1,175 @@
+"""GPU parity: every GEMM op of the surface vs the CPU oracle (oracle/dequant.py) on seeded
+inputs, through torch.ops.tinygemm -> C ABI -> CUDA kernels."""
+import pytest
+import torch
+
+from oracle import cases as C
+from oracle import dequant
+from tests import _tol
+
+pytestmark = pytest.mark.gpu
+
+GEMM_CASES = C.gemm_cases()
+
+
+def _dense_weight(c, inp):
+    dt = C.DT[c["dt"]]
+    n, g, fmt = c["n"], c["g"], c["fmt"]
+    if fmt == "f16":
+        return inp["w"]
+    if fmt == "int4":
+        return dequant.dequant_int4(inp["codes"], inp["sz"][:, :n], g, dt)
+    if fmt == "int8":
+        return dequant.dequant_int8(inp["codes"], inp["sz"][:, :n], g, dt)
+    if fmt == "any4g":
+        return dequant.dequant_lut(inp["codes"], inp["lut"], inp["sz"][:, :n], g, dt)
+    if fmt == "any4r":
+        return dequant.dequant_lut(inp["codes"], inp["lut"][:n], inp["sz"][:, :n], g, dt)
+    return dequant.dequant_mx4(inp["codes"], inp["exps"][:n], g, dt)
+
+
+@pytest.mark.parametrize("case", GEMM_CASES, ids=[C.case_id(c) for c in GEMM_CASES])
+def test_gemm_matches_oracle(case, cuda_device):
+    import tinygemm  # noqa: F401
+
+    inp = C.make_inputs(case)
+    got = C.run_ops(case, inp, cuda_device)["y"]
+    dt = C.DT[case["dt"]]
+    w = _dense_weight(case, inp)
+    x = inp["x"]
+    y64 = dequant.gemm_f64(x, w)
+    absdot = x.double().abs() @ w.double().abs().t()
+    assert got.shape == y64.shape and got.dtype == dt
+    assert torch.isfinite(got.float()).all()
+    nbad, worst = _tol.check_faithful(got, y64, absdot, dt)
+    assert nbad == 0, f"{nbad} elements outside the faithful-rounding bound (worst {worst:.2f}x)"
+    ref = dequant.gemm(x, w)
+    assert _tol.frob_rel(got, ref) <= _tol.FROB_REL
+    ulp = dequant.ulp_distance(got, ref)
+    assert (ulp == 0).double().mean().item() >= 0.95
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("fmt", ["int4", "any4g", "mx4", "int8"])
+@pytest.mark.parametrize("side", ["right", "left"])
+def test_identity_weight_is_exact(fmt, side, dt, cuda_device):
+    """The reference's strongest pin (tests/tinygemm/test_tinygemm_{int4,any4,mx4,int8}.py
+    test_identity_mul): W = I quantised with the test-side quantizer gives y == x bit-exactly in
+    bf16 (fp16 int4/int8 is knowingly inexact there: 15 * fp16(1/15) != 1, checked to 1e-3)."""
+    import tinygemm  # noqa: F401
+    from any4_b200 import utils as host
+
+    if fmt == "mx4" and dt == "fp16":
+        pytest.skip("mx4 is bf16 only")
+    ops = torch.ops.tinygemm
+    tdt = C.DT[dt]
+    k = 256
+    right = side == "right"
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(5, k, generator=gen).to(tdt).to(cuda_device)
+    w = torch.eye(k, dtype=tdt, device=cuda_device)
+    g = 32
+    if fmt == "mx4":
+        codes, e = host.quantize_mx4(w, g)
+        w2 = (ops.convert_matrix_to_m16n8k16_Bint4_layout(codes, 4) if right
+              else ops.convert_matrix_to_m16n8k16_Aint4_layout(codes, 4))
+        A, B = (x, w2) if right else (w2, x)
+        y = ops.tinygemm_y_f16RM_x_f16RM_w_mx4TC(A, B, g, e, right)
+    elif fmt == "int8":
+        codes, sz = host.group_quantize_tensor(w, 8, g)
+        w2 = (ops.convert_matrix_to_m16n8k16_Bint8_layout(codes, 2) if right
+              else ops.convert_matrix_to_m16n8k16_Aint8_layout(codes, 2))
+        A, B = (x, w2) if right else (w2, x)
+        y = ops.tinygemm_y_f16RM_x_f16RM_w_int8TC(A, B, g, sz, right)
+    else:
+        codes, sz = host.group_quantize_tensor(w, 4, g)
+        w2 = (ops.convert_matrix_to_m16n8k16_Bint4_layout(codes, 4) if right
+              else ops.convert_matrix_to_m16n8k16_Aint4_layout(codes, 4))
+        A, B = (x, w2) if right else (w2, x)
+        if fmt == "int4":
+            y = ops.tinygemm_y_f16RM_x_f16RM_w_int4TC(A, B, g, sz, right)
+        else:
+            lut = (torch.arange(16, dtype=torch.float32) - 8).to(tdt).to(cuda_device)
+            y = ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(A, B, g, sz, lut, right)
+    if dt == "bf16" or fmt == "mx4":
+        assert torch.equal(y, x)
+    else:
+        assert (y.float() - x.float()).abs().max().item() < 5e-3
+
+
+def test_mx4_nan_exponent(cuda_device):
+    """reference: tests/tinygemm/test_tinygemm_mx4.py:443-506 - e = 254 stays finite, e = 255 gives NaN"""
+    import tinygemm  # noqa: F401
+    from any4_b200 import utils as host
+
+    ops = torch.ops.tinygemm
+    k = 32
+    x = torch.randn(5, k, dtype=torch.bfloat16, device=cuda_device)
+    w = torch.eye(k, dtype=torch.bfloat16, device=cuda_device)
+    codes, e = host.quantize_mx4(w, 32)
+    w2 = ops.convert_matrix_to_m16n8k16_Bint4_layout(codes, 2)
+    y = ops.tinygemm_y_f16RM_x_f16RM_w_mx4TC(x, w2, 32, e, True)
+    assert torch.equal(y, x)
+    e[0][0] = 254
+    y = ops.tinygemm_y_f16RM_x_f16RM_w_mx4TC(x, w2, 32, e, True)
+    assert not torch.isnan(y).any()
+    e[0][0] = 255
+    y = ops.tinygemm_y_f16RM_x_f16RM_w_mx4TC(x, w2, 32, e, True)
+    assert torch.isnan(y).any()
+
+
+def test_lut_is_honoured(cuda_device):
+    """reference: tests/tinygemm/test_tinygemm_any4.py:17-26 - negating LUT and scales together
+    must leave the product unchanged, proving the LUT (not a built-in int4 table) is used."""
+    import tinygemm  # noqa: F401
+    from any4_b200 import utils as host
+
+    ops = torch.ops.tinygemm
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 256, generator=gen).bfloat16().to(dev)
+    w = torch.randn(64, 256, generator=gen).bfloat16().to(dev)
+    codes, sz = host.group_quantize_tensor(w, 4, 64)
+    w2 = ops.convert_matrix_to_m16n8k16_Bint4_layout(codes, 4)
+    lut = (torch.arange(16, dtype=torch.float32) - 8).bfloat16().to(dev)
+    y_int4 = ops.tinygemm_y_f16RM_x_f16RM_w_int4TC(x, w2, 64, sz, True)
+    y_any4 = ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(x, w2, 64, sz, lut, True)
+    assert torch.equal(y_int4, y_any4)
+    sz_neg = sz.clone()
+    sz_neg[:, :, 0] *= -1
+    y_neg = ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(x, w2, 64, sz_neg, -lut, True)
+    assert torch.equal(y_neg, y_any4)
+
+
+def test_large_shape_linearity_and_rows(cuda_device):
+    """Full-size property checks at the BASELINE shape (4096 x 4096, g = 128), where the oracle is
+    too slow for every element: (a) 64 sampled output columns against the float64 oracle,
+    (b) row m of a batched call equals the m = 1 call on that row, (c) exact zero for x = 0."""
+    import tinygemm  # noqa: F401
+
+    ops = torch.ops.tinygemm
+    dev = cuda_device
+    n = k = 4096
+    g = 128
+    gen = torch.Generator().manual_seed(11)
+    codes = torch.randint(0, 16, (n, k), generator=gen, dtype=torch.int32)
+    lut = ((torch.rand(n, 16, generator=gen) * 15).sort(1).values.bfloat16() - 8)
+    sz = torch.stack([torch.rand(k // g, n, generator=gen) * 0.01 + 0.001,
+                      torch.randn(k // g, n, generator=gen) * 0.01], dim=2).bfloat16()
+    x = torch.randn(4, k, generator=gen).bfloat16()
+    w2 = ops.convert_matrix_to_m16n8k16_Bint4_layout(codes.to(dev), 4)
+    lut_d, sz_d, x_d = lut.to(dev), sz.to(dev), x.to(dev)
+    y1 = ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(x_d[:1].contiguous(), w2, g, sz_d, lut_d, True)
+    y4 = ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(x_d, w2, g, sz_d, lut_d, True)
+    rows = torch.randperm(n, generator=gen)[:64]
+    wd = dequant.dequant_lut(codes[rows], lut[rows], sz[:, rows], g, torch.bfloat16)
+    y64 = dequant.gemm_f64(x, wd)
+    absdot = x.double().abs() @ wd.double().abs().t()
+    nbad, worst = _tol.check_faithful(y4.cpu()[:, rows], y64, absdot, torch.bfloat16)
+    assert nbad == 0, (nbad, worst)
+    nbad, worst = _tol.check_faithful(y1.cpu()[:, rows], y64[:1], absdot[:1], torch.bfloat16)
+    assert nbad == 0, (nbad, worst)
+    # m = 1 and m = 4 paths use different mma operand roles: same value up to fp32 summation order
+    assert _tol.frob_rel(y4[:1].cpu(), y1.cpu()) <= _tol.FROB_REL
+    y0 = ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(torch.zeros_like(x_d[:1]), w2, g, sz_d, lut_d, True)
+    assert (y0 == 0).all()
