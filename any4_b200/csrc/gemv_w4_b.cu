@@ -40,19 +40,22 @@ namespace cg = cooperative_groups;
 namespace tg {
 namespace {
 
-constexpr int kWarps = 8;              // consumer warps per CTA (all warps consume)
-constexpr int kThreads = kWarps * 32;
-constexpr int kStages = 3;             // ring depth per warp
+constexpr int kWarps = 8;              // consumer warps; warp 8 is the TMA producer
+constexpr int kThreads = (kWarps + 1) * 32;
+constexpr int kConsumerThreads = kWarps * 32;
+constexpr int kStages = 5;             // CTA-wide ring depth (80 KB of weights in flight per SM)
 constexpr int kRowsPerCta = 32;        // = 4 n-tiles
-constexpr int kChunkK = 128;           // k elements per ring stage
-constexpr int kTileChunkBytes = 512;   // bytes of one n-tile (8 rows) per stage: 8 * 128 / 2
-constexpr int kStageWBytes = 4 * kTileChunkBytes;
+constexpr int kChunkK = 128;           // k elements one warp consumes per stage
+constexpr int kStageK = kWarps * kChunkK;          // 1024 k per stage
+constexpr int kTileStageBytes = kStageK * 4;       // one n-tile (8 rows) x 1024 k = 4 KiB = one bulk copy
+constexpr int kStageBytes = 4 * kTileStageBytes;   // 16 KiB
+constexpr int kTileChunkBytes = 512;   // bytes of one n-tile per 128 k
 constexpr uint32_t kTableBase = 0x10000u;       // shared-window address of the pair table (64 KiB aligned)
 constexpr uint32_t kTableBytes = 0x10000u;      // 256 entries * 256 B pitch
 constexpr uint32_t kXBase = kTableBase + 128u;  // activations live in the unused half of each 256 B line
-constexpr uint32_t kRedBase = kTableBase + kTableBytes;  // cross-warp reduction scratch
-constexpr uint32_t kRedBytes = kWarps * 4 * 32 * 4;      // [warp][4][32] fp32
-constexpr uint32_t kDynSmemBytes = kRedBase + kRedBytes; // requested dynamic smem (window base <= 1024)
+constexpr uint32_t kHighBase = kTableBase + kTableBytes;   // ring stages that do not fit below the table
+constexpr uint32_t kRedBytes = kWarps * 4 * 32 * 4;        // [warp][4][32] fp32 reduction scratch
+constexpr uint32_t kDynSmemBytes = kHighBase + kStages * kStageBytes + kRedBytes;  // worst case: all stages high
 constexpr int kMaxXBytes = 32768;      // capacity of the activation area
 
 struct Params {
@@ -212,13 +215,12 @@ struct Geo<8> {  // slice = [1 super-tile][32 lanes][4 words]; row g at +g*64
 // the kernel
 //   M1 = true : exactly one activation row, weights are the mma A operand (two k-sets)
 //   M1 = false: 1..4 activation rows, weights are the mma B operand
-// grid = (row blocks, splits), cluster = (1, splits, 1)
+// grid = (row blocks, splits), cluster = (1, splits, 1); block = 8 consumer warps + 1 producer warp
 // ---------------------------------------------------------------------------------------
 template <tg_dtype DT, int IK, bool M1>
 __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t dyn_base = smem_u32(smem_raw);
-  if (dyn_base > 1024u) __trap();  // layout below assumes the window starts within the first KiB
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -228,221 +230,232 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   const int rows_valid = min(kRowsPerCta, p.w_rows - row0);  // multiple of 8
   const int tiles_valid = rows_valid >> 3;
 
-  // k range of this CTA, in 128-wide chunks
+  // k range of this CTA in 128-wide chunks; a stage is 8 consecutive chunks (one per consumer warp)
   const int chunks_total = (p.k + kChunkK - 1) / kChunkK;
   const int chunks_per_split = (chunks_total + p.splits - 1) / p.splits;
   const int chunk_begin = split * chunks_per_split;
   const int chunk_end = min(chunks_total, chunk_begin + chunks_per_split);
-
-  const int groups_per_chunk = (kChunkK >> p.glog2) > 0 ? (kChunkK >> p.glog2) : 1;
-  const uint32_t stage_bytes = kStageWBytes + 128u * groups_per_chunk;
+  const int n_stage_iters = (max(chunk_end - chunk_begin, 0) + kWarps - 1) / kWarps;
   const int n_groups = p.k >> p.glog2;
 
   // ---- shared memory carve-up (window addresses) ----
-  const uint32_t bar_base = dyn_base;                                   // [kWarps][kStages] mbarriers
-  const uint32_t ring_base = (dyn_base + kWarps * kStages * 8 + 127u) & ~127u;
-  const uint32_t my_ring = ring_base + warp * kStages * stage_bytes;
-  const uint32_t my_bar = bar_base + warp * kStages * 8;
-
-  // ---- producer side: lane 0 of each warp feeds its own ring ----
-  auto issue_chunk = [&](int c, int stage) {
-    // c: absolute chunk index; caller guarantees c < chunk_end
-    const uint32_t bar = my_bar + stage * 8;
-    const uint32_t dst = my_ring + stage * stage_bytes;
-    const int k0 = c * kChunkK;
-    const int kvalid = min(kChunkK, p.k - k0);
-    const uint32_t wbytes = (uint32_t)(kvalid * 4);  // bytes per n-tile for kvalid k: 8 rows * kvalid / 2
-    uint32_t szbytes = 0;
-    int g0 = 0, ng = 0;
-    if (p.sz != nullptr) {
-      g0 = k0 >> p.glog2;
-      ng = min(groups_per_chunk, n_groups - g0);
-      szbytes = (uint32_t)(rows_valid * 4);
-    }
-    mbar_expect_tx(bar, wbytes * tiles_valid + szbytes * ng);
-    const uint8_t* src = p.w + (int64_t)(rb * 4) * p.tile_stride + (int64_t)k0 * 4;
-    for (int t = 0; t < tiles_valid; ++t) {
-      bulk_g2s(dst + t * kTileChunkBytes, src + t * p.tile_stride, wbytes, bar);
-    }
-    for (int g = 0; g < ng; ++g) {
-      bulk_g2s(dst + kStageWBytes + g * 128, p.sz + (int64_t)(g0 + g) * p.w_rows + row0, szbytes, bar);
-    }
+  //   [dyn_base, +256)        mbarriers: full[kStages], empty[kStages]
+  //   low stages              as many 16 KiB stages as fit below the table at 0x10000
+  //   [0x10000, 0x20000)      pair table (even 128 B half-lines) + permuted activations (odd half-lines)
+  //   [0x20000, ...)          remaining stages, then the reduction scratch
+  const uint32_t full_bar = dyn_base;
+  const uint32_t empty_bar = dyn_base + 8u * kStages;
+  const uint32_t low_base = (dyn_base + 256u + 127u) & ~127u;
+  const int n_low = low_base < kTableBase ? min(kStages, (int)((kTableBase - low_base) / kStageBytes)) : 0;
+  const uint32_t red_base = kHighBase + (uint32_t)(kStages - n_low) * kStageBytes;
+  auto stage_addr = [&](int s) -> uint32_t {
+    return s < n_low ? low_base + (uint32_t)s * kStageBytes : kHighBase + (uint32_t)(s - n_low) * kStageBytes;
   };
+  if (dyn_base + 384u > kTableBase) __trap();  // the carve-up needs the window to start below the table
 
-  if (lane == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(my_bar + s * 8, 1);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + s * 8, 1);
+      mbar_init(empty_bar + s * 8, kWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int s = 0; s < kStages; ++s) {
-      const int c = chunk_begin + warp + s * kWarps;
-      if (c < chunk_end) issue_chunk(c, s);
-    }
-  }
-
-  // ---- pair table: entry e of row L at kTableBase + e*256 + 4L;  warp w builds e in [32w, 32w+32) ----
-  {
-    const int row = min(row0 + lane, p.w_rows - 1);
-    const uint16_t* lrow = p.lut + (int64_t)row * p.lut_stride;
-    const uint4 t0 = *reinterpret_cast<const uint4*>(lrow);
-    const uint4 t1 = *reinterpret_cast<const uint4*>(lrow + 8);
-    const uint32_t tp_[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-    const uint32_t thi = *reinterpret_cast<const uint32_t*>(lrow + 2 * warp);  // (T[2w], T[2w+1])
-    const uint32_t dst = kTableBase + (uint32_t)(warp * 32) * 256u + 4u * lane;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-#pragma unroll
-      for (int lo = 0; lo < 16; ++lo) {
-        const uint32_t sel = (h ? 0x7600u : 0x5400u) | ((lo & 1) ? 0x32u : 0x10u);
-        sts32(dst + (uint32_t)(h * 16 + lo) * 256u, prmt(tp_[lo >> 1], thi, sel));
-      }
-    }
-  }
-
-  // ---- activations, permuted so that (x[16t+i], x[16t+i+8]) are adjacent:
-  //      xp[16t + 2i] = x[16t + i], xp[16t + 2i + 1] = x[16t + i + 8], i = 0..7
-  //      linear byte offset o of row r lives at kXBase + ((r*x_row_bytes + o) / 128) * 256 + (o % 128)
-  {
-    const int items_per_row = p.k >> 2;  // one item = 4 k values of one tile = 8 output bytes
-    for (int r = 0; r < p.m; ++r) {
-      const uint32_t* xr = reinterpret_cast<const uint32_t*>(p.x + (int64_t)r * p.k);
-      for (int it = threadIdx.x; it < items_per_row; it += kThreads) {
-        const int t = it >> 2, pp = it & 3;
-        const uint32_t x1 = xr[t * 8 + pp];      // x[16t + 2pp], x[16t + 2pp + 1]
-        const uint32_t x2 = xr[t * 8 + 4 + pp];  // x[16t + 8 + 2pp], x[16t + 9 + 2pp]
-        const uint32_t o = (uint32_t)r * p.x_row_bytes + (uint32_t)it * 8u;
-        sts64(kXBase + (o >> 7) * 256u + (o & 127u), prmt(x1, x2, 0x5410u), prmt(x1, x2, 0x7632u));
-      }
-    }
   }
   __syncthreads();
 
-  // ---- main loop ----
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  float accb[4] = {0.f, 0.f, 0.f, 0.f};  // second, independent accumulation chain
-  const uint32_t lanebase = kTableBase | (uint32_t)(lane * 4);
-  const int g_ = lane >> 2, q_ = lane & 3;
-  // lanes that carry activations in the block-structured operand
-  const bool set1 = (g_ == q_);          // lanes 0, 5, 10, 15
-  const bool set2 = (g_ == q_ + 4);      // lanes 16, 21, 26, 31
-  const uint32_t x_active = (set1 || set2) ? 1u : 0u;
-  // M1: set1 lanes read tile t0, set2 lanes tile t0+1 (+32 B).  !M1: set1 rows {0,2}, set2 rows {1,3}
-  uint32_t x_lane_off;
-  if constexpr (M1) {
-    x_lane_off = set2 ? 32u : 0u;
+  if (warp == kWarps) {
+    // =========================== TMA producer (one elected lane) ===========================
+    if (lane == 0) {
+      const uint8_t* wsrc = p.w + (int64_t)(rb * 4) * p.tile_stride;
+      for (int j = 0; j < n_stage_iters; ++j) {
+        const int s = j % kStages;
+        if (j >= kStages) mbar_wait(empty_bar + s * 8, (uint32_t)(j / kStages - 1) & 1u);
+        const int c0 = chunk_begin + j * kWarps;
+        const int k0 = c0 * kChunkK;
+        const int kvalid = min(min(kStageK, (chunk_end - c0) * kChunkK), p.k - k0);
+        const uint32_t bytes = (uint32_t)kvalid * 4u;  // per n-tile: 8 rows * kvalid / 2
+        const uint32_t bar = full_bar + s * 8;
+        mbar_expect_tx(bar, bytes * (uint32_t)tiles_valid);
+        const uint32_t dst = stage_addr(s);
+        for (int t = 0; t < tiles_valid; ++t)
+          bulk_g2s(dst + t * kTileStageBytes, wsrc + t * p.tile_stride + (int64_t)k0 * 4, bytes, bar);
+      }
+    }
   } else {
-    const uint32_t o = set2 ? (uint32_t)p.x_row_bytes : 0u;
-    x_lane_off = (o >> 7) * 256u + (o & 127u);
-  }
-  // second pair of rows (mi + 2) for the !M1 kernel
-  const uint32_t x_row2 = ((2u * (uint32_t)p.x_row_bytes) >> 7) * 256u;  // x_row_bytes % 128 == 0
-  const bool has_row01 = M1 ? true : (set1 || p.m > 1);
-  const bool has_row23 = M1 ? false : (set1 ? p.m > 2 : p.m > 3);
-  const uint32_t xa01 = (x_active && has_row01) ? 1u : 0u;
-  const uint32_t xa23 = (x_active && has_row23) ? 1u : 0u;
-
-  const uint32_t w_lane_off = (uint32_t)(lane >> 3) * kTileChunkBytes + (uint32_t)(lane & 7) * Geo<IK>::kRowStride;
-  const uint32_t sz_lane_off = kStageWBytes + (uint32_t)lane * 4u;
-  const bool is_mx4 = (p.sz == nullptr);
-  const uint8_t* my_exps = is_mx4 ? p.exps + (int64_t)min(row0 + lane, p.w_rows - 1) * n_groups : nullptr;
-
-  uint32_t xr0[4] = {0u, 0u, 0u, 0u}, xr1[4] = {0u, 0u, 0u, 0u};  // x fragments (stay zero on inactive lanes)
-  uint32_t xs0[4] = {0u, 0u, 0u, 0u}, xs1[4] = {0u, 0u, 0u, 0u};  // rows mi+2 (!M1)
-
-  int it = 0;
-  for (int c = chunk_begin + warp; c < chunk_end; c += kWarps, ++it) {
-    const int stage = it % kStages;
-    const uint32_t parity = (uint32_t)(it / kStages) & 1u;
-    const uint32_t sbase = my_ring + stage * stage_bytes;
-    const int kvalid = min(kChunkK, p.k - c * kChunkK);
-
-    // group scale / zero for the four tile pairs (32 k each) of this chunk
-    uint32_t s2[4], z2[4];
-    if (is_mx4) {
-      const int g0 = (c * kChunkK) >> p.glog2;
+    // =========================== consumers ===========================
+    // ---- pair table: entry e of row L at kTableBase + e*256 + 4L;  warp w builds e in [32w, 32w+32) ----
+    {
+      const int row = min(row0 + lane, p.w_rows - 1);
+      const uint16_t* lrow = p.lut + (int64_t)row * p.lut_stride;
+      const uint4 t0 = *reinterpret_cast<const uint4*>(lrow);
+      const uint4 t1 = *reinterpret_cast<const uint4*>(lrow + 8);
+      const uint32_t tp_[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+      const uint32_t thi = *reinterpret_cast<const uint32_t*>(lrow + 2 * warp);  // (T[2w], T[2w+1])
+      const uint32_t dst = kTableBase + (uint32_t)(warp * 32) * 256u + 4u * lane;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int gi = min(g0 + ((t * 32) >> p.glog2), n_groups - 1);
-        const uint32_t s = e8m0_to_dt<DT>((uint32_t)my_exps[gi]);
-        s2[t] = s | (s << 16);
-        z2[t] = 0x80008000u;  // -0: fma(v, s, -0) == v * s including the sign of zero
-      }
-    }
-    mbar_wait(my_bar + stage * 8, parity);
-    if (!is_mx4) {
+      for (int h = 0; h < 2; ++h) {
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const uint32_t v = lds32(sbase + sz_lane_off + (uint32_t)((t * 32) >> p.glog2) * 128u);
-        s2[t] = prmt(v, v, 0x1010u);
-        z2[t] = prmt(v, v, 0x3232u);
-      }
-    }
-
-    // x base for this chunk: tile t0 = 8c + 2tp ; byte offset 32*t0 -> piece (t0/4), within (t0%4)*32
-    const uint32_t xc = kXBase + (uint32_t)c * 512u + x_lane_off;
-
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (u * 32 < kvalid) {  // warp-uniform tail guard (k % 128 != 0)
-        const uint4 wv = lds128(sbase + w_lane_off + Geo<IK>::unit_off(u));
-        const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int q = Geo<IK>::q(u, i);
-          const int tp = Geo<IK>::tp(u, i);
-          const uint32_t w = ww[i];
-          // byte0: tile 2tp (k0, k0+8)   byte2: tile 2tp (k0+1, k0+9)
-          // byte1: tile 2tp+1 (k0, k0+8) byte3: tile 2tp+1 (k0+1, k0+9)
-          uint32_t p0 = lds32(prmt(w, lanebase, 0x7604u));
-          uint32_t p1 = lds32(prmt(w, lanebase, 0x7614u));
-          uint32_t p2 = lds32(prmt(w, lanebase, 0x7624u));
-          uint32_t p3 = lds32(prmt(w, lanebase, 0x7634u));
-          p0 = fma2<DT>(p0, s2[tp], z2[tp]);
-          p1 = fma2<DT>(p1, s2[tp], z2[tp]);
-          p2 = fma2<DT>(p2, s2[tp], z2[tp]);
-          p3 = fma2<DT>(p3, s2[tp], z2[tp]);
-          // x for tile 2tp, slot q: bytes (tp/2)*256 + (tp%2)*64 + 8q of this chunk's x
-          const uint32_t xo = xc + (uint32_t)((tp >> 1) * 256 + (tp & 1) * 64 + q * 8);
-          if constexpr (M1) {
-            lds64_if(xr0[i], xr1[i], xo, x_active);
-            // A = weights: a0/a2 = k-set 1 (tile 2tp), a1/a3 = k-set 2 (tile 2tp+1)
-            mma16816<DT>((i & 1) ? accb : acc, p0, p1, p2, p3, xr0[i], xr1[i]);
-          } else {
-            float(&accA)[4] = (i & 1) ? accb : acc;
-            lds64_if(xr0[i], xr1[i], xo, xa01);
-            lds64_if(xs0[i], xs1[i], xo + x_row2, xa23);
-            // tile 2tp: B = (byte0, byte2); A = x (a0,a2 rows mi, a1,a3 rows mi+2)
-            mma16816<DT>(accA, xr0[i], xs0[i], xr1[i], xs1[i], p0, p2);
-            uint32_t y0 = 0u, y1 = 0u, v0 = 0u, v1 = 0u;
-            lds64_if(y0, y1, xo + 32u, xa01);
-            lds64_if(v0, v1, xo + 32u + x_row2, xa23);
-            mma16816<DT>(accA, y0, v0, y1, v1, p1, p3);
-          }
+        for (int lo = 0; lo < 16; ++lo) {
+          const uint32_t sel = (h ? 0x7600u : 0x5400u) | ((lo & 1) ? 0x32u : 0x10u);
+          sts32(dst + (uint32_t)(h * 16 + lo) * 256u, prmt(tp_[lo >> 1], thi, sel));
         }
       }
     }
 
-    // refill this stage with the chunk kStages rounds ahead
-    __syncwarp();
-    const int cn = c + kStages * kWarps;
-    if (lane == 0 && cn < chunk_end) issue_chunk(cn, stage);
-  }
+    // ---- activations, permuted so that (x[16t+i], x[16t+i+8]) are adjacent:
+    //      xp[16t + 2i] = x[16t + i], xp[16t + 2i + 1] = x[16t + i + 8], i = 0..7
+    //      linear byte offset o of row r lives at kXBase + ((r*x_row_bytes + o) / 128) * 256 + (o % 128)
+    {
+      const int item_begin = chunk_begin * (kChunkK >> 2);  // one item = 4 k values of one tile = 8 bytes
+      const int item_end = min(chunk_end * (kChunkK >> 2), p.k >> 2);
+      for (int r = 0; r < p.m; ++r) {
+        const uint32_t* xr = reinterpret_cast<const uint32_t*>(p.x + (int64_t)r * p.k);
+        for (int it = item_begin + (int)threadIdx.x; it < item_end; it += kConsumerThreads) {
+          const int t = it >> 2, pp = it & 3;
+          const uint32_t x1 = xr[t * 8 + pp];      // x[16t + 2pp], x[16t + 2pp + 1]
+          const uint32_t x2 = xr[t * 8 + 4 + pp];  // x[16t + 8 + 2pp], x[16t + 9 + 2pp]
+          const uint32_t o = (uint32_t)r * p.x_row_bytes + (uint32_t)it * 8u;
+          sts64(kXBase + (o >> 7) * 256u + (o & 127u), prmt(x1, x2, 0x5410u), prmt(x1, x2, 0x7632u));
+        }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");  // consumers only
 
-  // ---- epilogue: cross-warp (and cross-CTA) reduction, one rounding, store ----
+    // ---- main loop ----
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float accb[4] = {0.f, 0.f, 0.f, 0.f};  // second, independent accumulation chain
+    const uint32_t lanebase = kTableBase | (uint32_t)(lane * 4);
+    const int g_ = lane >> 2, q_ = lane & 3;
+    // lanes that carry activations in the block-structured operand
+    const bool set1 = (g_ == q_);          // lanes 0, 5, 10, 15
+    const bool set2 = (g_ == q_ + 4);      // lanes 16, 21, 26, 31
+    const uint32_t x_active = (set1 || set2) ? 1u : 0u;
+    // M1: set1 lanes read tile t0, set2 lanes tile t0+1 (+32 B).  !M1: set1 rows {0,2}, set2 rows {1,3}
+    uint32_t x_lane_off;
+    if constexpr (M1) {
+      x_lane_off = set2 ? 32u : 0u;
+    } else {
+      const uint32_t o = set2 ? (uint32_t)p.x_row_bytes : 0u;
+      x_lane_off = (o >> 7) * 256u;  // x_row_bytes % 128 == 0
+    }
+    const uint32_t x_row2 = ((2u * (uint32_t)p.x_row_bytes) >> 7) * 256u;  // rows mi + 2 (!M1)
+    const bool has_row01 = M1 ? true : (set1 || p.m > 1);
+    const bool has_row23 = M1 ? false : (set1 ? p.m > 2 : p.m > 3);
+    const uint32_t xa01 = (x_active && has_row01) ? 1u : 0u;
+    const uint32_t xa23 = (x_active && has_row23) ? 1u : 0u;
+
+    const uint32_t w_lane_off = (uint32_t)(lane >> 3) * kTileStageBytes + (uint32_t)warp * kTileChunkBytes +
+                                (uint32_t)(lane & 7) * Geo<IK>::kRowStride;
+    const bool is_mx4 = (p.sz == nullptr);
+    const int my_row = min(row0 + lane, p.w_rows - 1);
+    const uint8_t* my_exps = is_mx4 ? p.exps + (int64_t)my_row * n_groups : nullptr;
+    const uint32_t* my_sz = is_mx4 ? nullptr : p.sz + my_row;
+    const int groups_per_chunk = max(1, kChunkK >> p.glog2);
+
+    // raw group data of a 128-k chunk: (scale, zero) words, or e8m0 bytes for mx4; fetched one stage ahead
+    auto fetch_groups = [&](int c, uint32_t (&raw)[4]) {
+      if (c >= chunk_end) return;
+      const int g0 = (c * kChunkK) >> p.glog2;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i] += accb[i];
-  // red[warp][j][row] fp32 at kRedBase
-  {
-    const uint32_t rbase = kRedBase + (uint32_t)warp * 512u;
+      for (int t = 0; t < 4; ++t) {
+        if (t < groups_per_chunk) {
+          const int gi = min(g0 + t, n_groups - 1);
+          raw[t] = is_mx4 ? (uint32_t)my_exps[gi] : my_sz[(int64_t)gi * p.w_rows];
+        }
+      }
+    };
+
+    uint32_t xr0[4] = {0u, 0u, 0u, 0u}, xr1[4] = {0u, 0u, 0u, 0u};  // x fragments (stay zero on inactive lanes)
+    uint32_t xs0[4] = {0u, 0u, 0u, 0u}, xs1[4] = {0u, 0u, 0u, 0u};  // rows mi+2 (!M1)
+    uint32_t graw[4] = {0u, 0u, 0u, 0u}, gnext[4] = {0u, 0u, 0u, 0u};
+    fetch_groups(chunk_begin + warp, graw);
+
+    for (int j = 0; j < n_stage_iters; ++j) {
+      const int s = j % kStages;
+      const int c = chunk_begin + j * kWarps + warp;  // this warp's chunk in stage j
+      fetch_groups(c + kWarps, gnext);                // prefetch next stage's scale / zero
+      const int kvalid = c < chunk_end ? min(kChunkK, p.k - c * kChunkK) : 0;
+
+      // group scale / zero for the four tile pairs (32 k each) of this chunk
+      uint32_t s2[4], z2[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        // group of tile pair t inside the chunk: t (g=32), t/2 (g=64), 0 (g>=128) - no dynamic indexing
+        const uint32_t v = p.glog2 == 5 ? graw[t] : (p.glog2 == 6 ? graw[t >> 1] : graw[0]);
+        if (is_mx4) {
+          const uint32_t sc = e8m0_to_dt<DT>(v);
+          s2[t] = sc | (sc << 16);
+          z2[t] = 0x80008000u;  // -0: fma(v, s, -0) == v * s including the sign of zero
+        } else {
+          s2[t] = prmt(v, v, 0x1010u);
+          z2[t] = prmt(v, v, 0x3232u);
+        }
+      }
+
+      mbar_wait(full_bar + s * 8, (uint32_t)(j / kStages) & 1u);
+      const uint32_t sbase = stage_addr(s) + w_lane_off;
+      // x base for this chunk: tile t0 = 8c + 2tp ; byte offset 32*t0 -> piece (t0/4), within (t0%4)*32
+      const uint32_t xc = kXBase + (uint32_t)c * 512u + x_lane_off;
+
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (u * 32 < kvalid) {  // warp-uniform tail guard (k % 128 != 0, or no chunk for this warp)
+          const uint4 wv = lds128(sbase + Geo<IK>::unit_off(u));
+          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int q = Geo<IK>::q(u, i);
+            const int tp = Geo<IK>::tp(u, i);
+            const uint32_t w = ww[i];
+            // byte0: tile 2tp (k0, k0+8)   byte2: tile 2tp (k0+1, k0+9)
+            // byte1: tile 2tp+1 (k0, k0+8) byte3: tile 2tp+1 (k0+1, k0+9)
+            uint32_t p0 = lds32(prmt(w, lanebase, 0x7604u));
+            uint32_t p1 = lds32(prmt(w, lanebase, 0x7614u));
+            uint32_t p2 = lds32(prmt(w, lanebase, 0x7624u));
+            uint32_t p3 = lds32(prmt(w, lanebase, 0x7634u));
+            p0 = fma2<DT>(p0, s2[tp], z2[tp]);
+            p1 = fma2<DT>(p1, s2[tp], z2[tp]);
+            p2 = fma2<DT>(p2, s2[tp], z2[tp]);
+            p3 = fma2<DT>(p3, s2[tp], z2[tp]);
+            // x for tile 2tp, slot q: bytes (tp/2)*256 + (tp%2)*64 + 8q of this chunk's x
+            const uint32_t xo = xc + (uint32_t)((tp >> 1) * 256 + (tp & 1) * 64 + q * 8);
+            if constexpr (M1) {
+              lds64_if(xr0[i], xr1[i], xo, x_active);
+              // A = weights: a0/a2 = k-set 1 (tile 2tp), a1/a3 = k-set 2 (tile 2tp+1)
+              mma16816<DT>((i & 1) ? accb : acc, p0, p1, p2, p3, xr0[i], xr1[i]);
+            } else {
+              float(&accA)[4] = (i & 1) ? accb : acc;
+              lds64_if(xr0[i], xr1[i], xo, xa01);
+              lds64_if(xs0[i], xs1[i], xo + x_row2, xa23);
+              // tile 2tp: B = (byte0, byte2); A = x (a0,a2 rows mi, a1,a3 rows mi+2)
+              mma16816<DT>(accA, xr0[i], xs0[i], xr1[i], xs1[i], p0, p2);
+              uint32_t y0 = 0u, y1 = 0u, v0 = 0u, v1 = 0u;
+              lds64_if(y0, y1, xo + 32u, xa01);
+              lds64_if(v0, v1, xo + 32u + x_row2, xa23);
+              mma16816<DT>(accA, y0, v0, y1, v1, p1, p3);
+            }
+          }
+        }
+      }
+
+      // hand the stage back to the producer
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar + s * 8) : "memory");
+#pragma unroll
+      for (int t = 0; t < 4; ++t) graw[t] = gnext[t];
+    }
+
+    // ---- per-warp partial results -> red[warp][j][row] fp32 ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] += accb[i];
+    const uint32_t rbase = red_base + (uint32_t)warp * 512u;
     if constexpr (M1) {
       // valid: lanes q_<2: acc[0],acc[1] = rows 4g+2q_, 4g+2q_+1 (k-set 1); lanes q_>=2: acc[2],acc[3] = rows
       // 4g+2(q_-2), +1 (k-set 2)
-      const int j = q_ >> 1;
+      const int jj = q_ >> 1;
       const int r = 4 * g_ + 2 * (q_ & 1);
-      const float v0 = j ? acc[2] : acc[0];
-      const float v1 = j ? acc[3] : acc[1];
-      sts32(rbase + (uint32_t)(j * 32 + r) * 4u, __float_as_uint(v0));
-      sts32(rbase + (uint32_t)(j * 32 + r + 1) * 4u, __float_as_uint(v1));
-      // slots j = 2, 3 unused
+      sts32(rbase + (uint32_t)(jj * 32 + r) * 4u, __float_as_uint(jj ? acc[2] : acc[0]));
+      sts32(rbase + (uint32_t)(jj * 32 + r + 1) * 4u, __float_as_uint(jj ? acc[3] : acc[1]));
     } else {
       // acc[0],acc[1] = C[g_][2q_, 2q_+1]: mi = g_/4, rows 4*(2q_)+g_%4 and 4*(2q_+1)+g_%4; acc[2],acc[3]: mi + 2
       const int mi = g_ >> 2, qq = g_ & 3;
@@ -454,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   }
   __syncthreads();
 
-  // CTA-level sums: thread (j, row) -> sum over warps, written back to red[0][j][row]
+  // ---- CTA-level sums: thread (tj, trow) adds the 8 warps' partials in warp order ----
   const int nj = M1 ? 1 : p.m;
   float total = 0.f;
   const int tj = threadIdx.x >> 5, trow = threadIdx.x & 31;
@@ -463,14 +476,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       if (tj == 0) {
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
-          total += __uint_as_float(lds32(kRedBase + (uint32_t)w * 512u + (uint32_t)trow * 4u));
-          total += __uint_as_float(lds32(kRedBase + (uint32_t)w * 512u + (uint32_t)(32 + trow) * 4u));
+          total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)trow * 4u));
+          total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)(32 + trow) * 4u));
         }
       }
     } else {
 #pragma unroll
       for (int w = 0; w < kWarps; ++w)
-        total += __uint_as_float(lds32(kRedBase + (uint32_t)w * 512u + (uint32_t)(tj * 32 + trow) * 4u));
+        total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)(tj * 32 + trow) * 4u));
     }
   }
 
@@ -483,12 +496,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   // split-k: every CTA of the cluster publishes its 32 x nj partials; rank 0 adds them in rank order
   cg::cluster_group cluster = cg::this_cluster();
   __syncthreads();  // everyone is done reading red[] of all warps
-  float* part = reinterpret_cast<float*>(smem_raw + (kRedBase - dyn_base));
+  float* part = reinterpret_cast<float*>(smem_raw + (red_base - dyn_base));
   if (threadIdx.x < 128) part[tj * 32 + trow] = total;
   cluster.sync();
   if (cluster.block_rank() == 0 && threadIdx.x < 128 && tj < nj) {
     float sum = total;
-    for (int r = 1; r < p.splits; ++r) {
+    for (unsigned r = 1; r < (unsigned)p.splits; ++r) {
       const float* remote = cluster.map_shared_rank(part, r);
       sum += remote[tj * 32 + trow];
     }

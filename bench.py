@@ -108,12 +108,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def time_gemv_set(call, n_calls_per_step, steps, warmup, dist=None):
+def time_gemv_set(call, n_calls_per_step, steps, warmup, dist=None, graph=False):
     """W untimed steps, then exactly K timed steps bracketed by barrier + synchronize; CUDA events
-    on the launching (current) stream; returns max-over-ranks milliseconds for the K steps."""
+    on the launching (current) stream; returns max-over-ranks milliseconds for the K steps.
+    graph=True captures one step in a CUDA graph (after the eager warm-up) and replays it K times:
+    the ~2 us GEMV is shorter than an eager launch, so only a graph measures the GPU, not the host."""
     for _ in range(warmup):
         call()
     torch.cuda.synchronize()
+    if graph:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            call()
+        eager_call, call = call, g.replay
+        call()
+        torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
         torch.cuda.synchronize()
@@ -240,8 +249,9 @@ def run_ours(args):
                 ys[0] = lin(x)
 
         lib.tg_reset_launch_count()
-        ms = time_gemv_set(step, copies, steps, warmup, dist)
-        launches = int(lib.tg_launch_count()) * steps // (steps + warmup)
+        step()
+        launches = int(lib.tg_launch_count()) * steps  # our kernels per step (same under graph replay) x K
+        ms = time_gemv_set(step, copies, steps, warmup, dist, graph=(world == 1 and not args.no_graph))
         out = {"n": n, "k": k, "copies": copies, "ms": ms, "launches": launches,
                "us_per_gemv": ms * 1e3 / (steps * copies),
                "gbps": nbytes * copies * steps / (ms * 1e-3) / 1e9}
@@ -285,6 +295,7 @@ def run_ours(args):
             "config": {
                 "workload": "any4-bf16 GEMV m=1 n=k=4096 g=128 per-row LUT (BASELINE configs[1])",
                 "gemvs_per_step": head["copies"],
+                "launch": "eager" if (args.no_graph or world > 1) else "one CUDA graph per step (replayed K times)",
                 "l2_policy": f"inputs larger than L2: {head['copies']} distinct weight sets = "
                              f"{head['copies'] * nbytes / 1e6:.0f} MB rotated every step",
                 "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world} + NCCL all-reduce on y",
@@ -314,6 +325,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

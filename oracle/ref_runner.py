@@ -63,15 +63,22 @@ def bench(n, k, iters):
         layers.append((w, lut, sz))
     x = torch.randn(1, k, device=dev).bfloat16()
     op = torch.ops.tinygemm.tinygemm_y_f16RM_x_f16RM_w_any4TC
-    for _ in range(3):
+    def step():
         for w, lut, sz in layers:
             op(x, w, g, sz, lut, True)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()  # same protocol as bench.py: one graph per step, replayed
+    with torch.cuda.graph(graph):
+        step()
+    graph.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        for w, lut, sz in layers:
-            op(x, w, g, sz, lut, True)
+        graph.replay()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (iters * copies)
