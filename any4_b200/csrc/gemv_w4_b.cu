@@ -50,13 +50,23 @@ constexpr int kStageK = kWarps * kChunkK;          // 1024 k per stage
 constexpr int kTileStageBytes = kStageK * 4;       // one n-tile (8 rows) x 1024 k = 4 KiB = one bulk copy
 constexpr int kStageBytes = 4 * kTileStageBytes;   // 16 KiB
 constexpr int kTileChunkBytes = 512;   // bytes of one n-tile per 128 k
-constexpr uint32_t kTableBase = 0x10000u;       // shared-window address of the pair table (64 KiB aligned)
+// Shared-memory carve-up, all relative to the start W0 of the CTA's dynamic window (which is NOT
+// 0-based for CTAs of a cluster):
+//   [W0, +256)            mbarriers full[kStages], empty[kStages]
+//   [W0+256, +768)        split-k exchange buffer (same offset in every CTA of the cluster: DSMEM)
+//   [W0+1024, T)          as many 16 KiB ring stages as fit below the table
+//   [T, T+64K)            pair table, T = first 64 KiB-aligned address >= W0+1024; entry pitch 256 B:
+//                         even 128 B half-lines = table, odd half-lines = permuted activations
+//   [T+64K, ...)          remaining ring stages, group scale/zero words, reduction scratch
+constexpr uint32_t kCtrlBytes = 1024u;
+constexpr uint32_t kExchOff = 256u;
 constexpr uint32_t kTableBytes = 0x10000u;      // 256 entries * 256 B pitch
-constexpr uint32_t kXBase = kTableBase + 128u;  // activations live in the unused half of each 256 B line
-constexpr uint32_t kHighBase = kTableBase + kTableBytes;   // ring stages that do not fit below the table
+constexpr uint32_t kSzBytes = 32768u;           // staged (scale, zero) words: 256 groups x 32 rows
 constexpr uint32_t kRedBytes = kWarps * 4 * 32 * 4;        // [warp][4][32] fp32 reduction scratch
-constexpr uint32_t kDynSmemBytes = kHighBase + kStages * kStageBytes + kRedBytes;  // worst case: all stages high
-constexpr int kMaxXBytes = 32768;      // capacity of the activation area
+// worst case over the alignment of W0: control + < 16 KiB unusable + table + all stages + sz + red
+constexpr uint32_t kDynSmemBytes = kCtrlBytes + kStageBytes + kTableBytes + kStages * kStageBytes + kSzBytes + kRedBytes;
+constexpr int kMaxXBytes = 32768;      // capacity of the activation area (odd half-lines of the table)
+constexpr int kPre = 4;                // x items / sz words per thread whose loads are issued before the TMA starts
 
 struct Params {
   const uint8_t* w;      // packed weight
@@ -238,20 +248,60 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   const int n_stage_iters = (max(chunk_end - chunk_begin, 0) + kWarps - 1) / kWarps;
   const int n_groups = p.k >> p.glog2;
 
-  // ---- shared memory carve-up (window addresses) ----
-  //   [dyn_base, +256)        mbarriers: full[kStages], empty[kStages]
-  //   low stages              as many 16 KiB stages as fit below the table at 0x10000
-  //   [0x10000, 0x20000)      pair table (even 128 B half-lines) + permuted activations (odd half-lines)
-  //   [0x20000, ...)          remaining stages, then the reduction scratch
+  // ---- shared memory carve-up (window addresses, see the constants above) ----
   const uint32_t full_bar = dyn_base;
   const uint32_t empty_bar = dyn_base + 8u * kStages;
-  const uint32_t low_base = (dyn_base + 256u + 127u) & ~127u;
-  const int n_low = low_base < kTableBase ? min(kStages, (int)((kTableBase - low_base) / kStageBytes)) : 0;
-  const uint32_t red_base = kHighBase + (uint32_t)(kStages - n_low) * kStageBytes;
+  const uint32_t low_base = dyn_base + kCtrlBytes;
+  const uint32_t table_base = (low_base + 0xffffu) & ~0xffffu;
+  const uint32_t x_base = table_base + 128u;
+  const uint32_t high_base = table_base + kTableBytes;
+  const int n_low = min(kStages, (int)((table_base - low_base) / kStageBytes));
+  const uint32_t sz_base = high_base + (uint32_t)(kStages - n_low) * kStageBytes;
+  const uint32_t red_base = sz_base + kSzBytes;
   auto stage_addr = [&](int s) -> uint32_t {
-    return s < n_low ? low_base + (uint32_t)s * kStageBytes : kHighBase + (uint32_t)(s - n_low) * kStageBytes;
+    return s < n_low ? low_base + (uint32_t)s * kStageBytes : high_base + (uint32_t)(s - n_low) * kStageBytes;
   };
-  if (dyn_base + 384u > kTableBase) __trap();  // the carve-up needs the window to start below the table
+
+  // group scale/zero of this CTA's k range are staged in shared memory when they fit
+  const int group_first = (chunk_begin * kChunkK) >> p.glog2;
+  const int group_last = chunk_end > chunk_begin ? (min(chunk_end * kChunkK, p.k) - 1) >> p.glog2 : group_first;
+  const int n_groups_cta = group_last - group_first + 1;
+  const bool sz_staged = (uint32_t)n_groups_cta * 128u <= kSzBytes;
+  const bool is_mx4 = (p.sz == nullptr);
+
+  // ---- consumers issue their small global loads (LUT row, first activations, first scale/zero words)
+  //      BEFORE the bulk weight stream is started, so they are not queued behind it in the memory system
+  uint4 lut0 = make_uint4(0, 0, 0, 0), lut1 = lut0;
+  uint32_t lut_hi = 0;
+  uint32_t px1[kPre], px2[kPre], psz[kPre];
+  const int item_begin = chunk_begin * (kChunkK >> 2);  // one x item = 4 k values of one tile = 8 staged bytes
+  const int item_end = min(chunk_end * (kChunkK >> 2), p.k >> 2);
+  const int sz_words = sz_staged ? n_groups_cta * 32 : 0;
+  auto load_sz_word = [&](int i) -> uint32_t {  // word i = (group i / 32, row i % 32) of this CTA
+    const int gi = group_first + (i >> 5);
+    const int row = min(row0 + (i & 31), p.w_rows - 1);
+    if (is_mx4) return e8m0_to_dt<DT>((uint32_t)p.exps[(int64_t)row * n_groups + gi]) | 0x80000000u;  // zero = -0
+    return p.sz[(int64_t)gi * p.w_rows + row];
+  };
+  if (warp < kWarps) {
+    const int row = min(row0 + lane, p.w_rows - 1);
+    const uint16_t* lrow = p.lut + (int64_t)row * p.lut_stride;
+    lut0 = *reinterpret_cast<const uint4*>(lrow);
+    lut1 = *reinterpret_cast<const uint4*>(lrow + 8);
+    lut_hi = *reinterpret_cast<const uint32_t*>(lrow + 2 * warp);  // (T[2w], T[2w+1])
+    const uint32_t* xr = reinterpret_cast<const uint32_t*>(p.x);   // row 0; further rows are loaded later
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) {
+      const int it = item_begin + (int)threadIdx.x + i * kConsumerThreads;
+      px1[i] = px2[i] = psz[i] = 0u;
+      if (it < item_end) {
+        px1[i] = xr[(it >> 2) * 8 + (it & 3)];
+        px2[i] = xr[(it >> 2) * 8 + 4 + (it & 3)];
+      }
+      const int w = (int)threadIdx.x + i * kConsumerThreads;
+      if (w < sz_words) psz[i] = load_sz_word(w);
+    }
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -283,48 +333,58 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     }
   } else {
     // =========================== consumers ===========================
-    // ---- pair table: entry e of row L at kTableBase + e*256 + 4L;  warp w builds e in [32w, 32w+32) ----
+    // ---- pair table: entry e of row L at table_base + e*256 + 4L;  warp w builds e in [32w, 32w+32) ----
     {
-      const int row = min(row0 + lane, p.w_rows - 1);
-      const uint16_t* lrow = p.lut + (int64_t)row * p.lut_stride;
-      const uint4 t0 = *reinterpret_cast<const uint4*>(lrow);
-      const uint4 t1 = *reinterpret_cast<const uint4*>(lrow + 8);
-      const uint32_t tp_[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-      const uint32_t thi = *reinterpret_cast<const uint32_t*>(lrow + 2 * warp);  // (T[2w], T[2w+1])
-      const uint32_t dst = kTableBase + (uint32_t)(warp * 32) * 256u + 4u * lane;
+      const uint32_t tp_[8] = {lut0.x, lut0.y, lut0.z, lut0.w, lut1.x, lut1.y, lut1.z, lut1.w};
+      const uint32_t dst = table_base + (uint32_t)(warp * 32) * 256u + 4u * lane;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
 #pragma unroll
         for (int lo = 0; lo < 16; ++lo) {
           const uint32_t sel = (h ? 0x7600u : 0x5400u) | ((lo & 1) ? 0x32u : 0x10u);
-          sts32(dst + (uint32_t)(h * 16 + lo) * 256u, prmt(tp_[lo >> 1], thi, sel));
+          sts32(dst + (uint32_t)(h * 16 + lo) * 256u, prmt(tp_[lo >> 1], lut_hi, sel));
         }
       }
     }
 
     // ---- activations, permuted so that (x[16t+i], x[16t+i+8]) are adjacent:
     //      xp[16t + 2i] = x[16t + i], xp[16t + 2i + 1] = x[16t + i + 8], i = 0..7
-    //      linear byte offset o of row r lives at kXBase + ((r*x_row_bytes + o) / 128) * 256 + (o % 128)
+    //      linear byte offset o of row r lives at x_base + ((r*x_row_bytes + o) / 128) * 256 + (o % 128)
     {
-      const int item_begin = chunk_begin * (kChunkK >> 2);  // one item = 4 k values of one tile = 8 bytes
-      const int item_end = min(chunk_end * (kChunkK >> 2), p.k >> 2);
+      auto put_x = [&](int r, int it, uint32_t x1, uint32_t x2) {
+        const uint32_t o = (uint32_t)r * p.x_row_bytes + (uint32_t)it * 8u;
+        sts64(x_base + (o >> 7) * 256u + (o & 127u), prmt(x1, x2, 0x5410u), prmt(x1, x2, 0x7632u));
+      };
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) {
+        const int it = item_begin + (int)threadIdx.x + i * kConsumerThreads;
+        if (it < item_end) put_x(0, it, px1[i], px2[i]);
+      }
       for (int r = 0; r < p.m; ++r) {
         const uint32_t* xr = reinterpret_cast<const uint32_t*>(p.x + (int64_t)r * p.k);
-        for (int it = item_begin + (int)threadIdx.x; it < item_end; it += kConsumerThreads) {
+        for (int it = item_begin + (int)threadIdx.x + (r == 0 ? kPre * kConsumerThreads : 0); it < item_end;
+             it += kConsumerThreads) {
           const int t = it >> 2, pp = it & 3;
-          const uint32_t x1 = xr[t * 8 + pp];      // x[16t + 2pp], x[16t + 2pp + 1]
-          const uint32_t x2 = xr[t * 8 + 4 + pp];  // x[16t + 8 + 2pp], x[16t + 9 + 2pp]
-          const uint32_t o = (uint32_t)r * p.x_row_bytes + (uint32_t)it * 8u;
-          sts64(kXBase + (o >> 7) * 256u + (o & 127u), prmt(x1, x2, 0x5410u), prmt(x1, x2, 0x7632u));
+          put_x(r, it, xr[t * 8 + pp], xr[t * 8 + 4 + pp]);
         }
       }
+    }
+    // ---- group (scale, zero) words: sz_s[group - group_first][row] ----
+    {
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) {
+        const int w = (int)threadIdx.x + i * kConsumerThreads;
+        if (w < sz_words) sts32(sz_base + (uint32_t)w * 4u, psz[i]);
+      }
+      for (int w = (int)threadIdx.x + kPre * kConsumerThreads; w < sz_words; w += kConsumerThreads)
+        sts32(sz_base + (uint32_t)w * 4u, load_sz_word(w));
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");  // consumers only
 
     // ---- main loop ----
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     float accb[4] = {0.f, 0.f, 0.f, 0.f};  // second, independent accumulation chain
-    const uint32_t lanebase = kTableBase | (uint32_t)(lane * 4);
+    const uint32_t lanebase = table_base | (uint32_t)(lane * 4);
     const int g_ = lane >> 2, q_ = lane & 3;
     // lanes that carry activations in the block-structured operand
     const bool set1 = (g_ == q_);          // lanes 0, 5, 10, 15
@@ -346,13 +406,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
 
     const uint32_t w_lane_off = (uint32_t)(lane >> 3) * kTileStageBytes + (uint32_t)warp * kTileChunkBytes +
                                 (uint32_t)(lane & 7) * Geo<IK>::kRowStride;
-    const bool is_mx4 = (p.sz == nullptr);
     const int my_row = min(row0 + lane, p.w_rows - 1);
-    const uint8_t* my_exps = is_mx4 ? p.exps + (int64_t)my_row * n_groups : nullptr;
-    const uint32_t* my_sz = is_mx4 ? nullptr : p.sz + my_row;
     const int groups_per_chunk = max(1, kChunkK >> p.glog2);
 
-    // raw group data of a 128-k chunk: (scale, zero) words, or e8m0 bytes for mx4; fetched one stage ahead
+    // (scale, zero) words of a 128-k chunk: from shared memory when staged, else straight from global one stage
+    // ahead (only for group counts beyond the staging capacity)
     auto fetch_groups = [&](int c, uint32_t (&raw)[4]) {
       if (c >= chunk_end) return;
       const int g0 = (c * kChunkK) >> p.glog2;
@@ -360,7 +418,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       for (int t = 0; t < 4; ++t) {
         if (t < groups_per_chunk) {
           const int gi = min(g0 + t, n_groups - 1);
-          raw[t] = is_mx4 ? (uint32_t)my_exps[gi] : my_sz[(int64_t)gi * p.w_rows];
+          if (sz_staged) {
+            raw[t] = lds32(sz_base + (uint32_t)((gi - group_first) * 32 + lane) * 4u);
+          } else if (is_mx4) {
+            raw[t] = e8m0_to_dt<DT>((uint32_t)p.exps[(int64_t)my_row * n_groups + gi]) | 0x80000000u;
+          } else {
+            raw[t] = p.sz[(int64_t)gi * p.w_rows + my_row];
+          }
         }
       }
     };
@@ -382,20 +446,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       for (int t = 0; t < 4; ++t) {
         // group of tile pair t inside the chunk: t (g=32), t/2 (g=64), 0 (g>=128) - no dynamic indexing
         const uint32_t v = p.glog2 == 5 ? graw[t] : (p.glog2 == 6 ? graw[t >> 1] : graw[0]);
-        if (is_mx4) {
-          const uint32_t sc = e8m0_to_dt<DT>(v);
-          s2[t] = sc | (sc << 16);
-          z2[t] = 0x80008000u;  // -0: fma(v, s, -0) == v * s including the sign of zero
-        } else {
-          s2[t] = prmt(v, v, 0x1010u);
-          z2[t] = prmt(v, v, 0x3232u);
-        }
+        s2[t] = prmt(v, v, 0x1010u);  // mx4 words carry zero = -0: fma(v, s, -0) == v * s incl. sign of zero
+        z2[t] = prmt(v, v, 0x3232u);
       }
 
       mbar_wait(full_bar + s * 8, (uint32_t)(j / kStages) & 1u);
       const uint32_t sbase = stage_addr(s) + w_lane_off;
       // x base for this chunk: tile t0 = 8c + 2tp ; byte offset 32*t0 -> piece (t0/4), within (t0%4)*32
-      const uint32_t xc = kXBase + (uint32_t)c * 512u + x_lane_off;
+      const uint32_t xc = x_base + (uint32_t)c * 512u + x_lane_off;
 
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -496,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   // split-k: every CTA of the cluster publishes its 32 x nj partials; rank 0 adds them in rank order
   cg::cluster_group cluster = cg::this_cluster();
   __syncthreads();  // everyone is done reading red[] of all warps
-  float* part = reinterpret_cast<float*>(smem_raw + (red_base - dyn_base));
+  float* part = reinterpret_cast<float*>(smem_raw + kExchOff);
   if (threadIdx.x < 128) part[tj * 32 + trow] = total;
   cluster.sync();
   if (cluster.block_rank() == 0 && threadIdx.x < 128 && tj < nj) {
