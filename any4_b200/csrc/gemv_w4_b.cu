@@ -40,33 +40,34 @@ namespace cg = cooperative_groups;
 namespace tg {
 namespace {
 
-constexpr int kWarps = 8;              // consumer warps; warp 8 is the TMA producer
+constexpr int kWarps = 16;             // consumer warps (4 per SM sub-partition); warp 16 is the TMA producer
 constexpr int kThreads = (kWarps + 1) * 32;
 constexpr int kConsumerThreads = kWarps * 32;
-constexpr int kStages = 5;             // CTA-wide ring depth (80 KB of weights in flight per SM)
+constexpr int kStages = 3;             // CTA-wide ring depth (96 KB of weights in flight per SM)
 constexpr int kRowsPerCta = 32;        // = 4 n-tiles
 constexpr int kChunkK = 128;           // k elements one warp consumes per stage
-constexpr int kStageK = kWarps * kChunkK;          // 1024 k per stage
-constexpr int kTileStageBytes = kStageK * 4;       // one n-tile (8 rows) x 1024 k = 4 KiB = one bulk copy
-constexpr int kStageBytes = 4 * kTileStageBytes;   // 16 KiB
+constexpr int kStageK = kWarps * kChunkK;          // 2048 k per stage
+constexpr int kTileStageBytes = kStageK * 4;       // one n-tile (8 rows) x 2048 k = 8 KiB = one bulk copy
+constexpr int kStageBytes = 4 * kTileStageBytes;   // 32 KiB
 constexpr int kTileChunkBytes = 512;   // bytes of one n-tile per 128 k
 // Shared-memory carve-up, all relative to the start W0 of the CTA's dynamic window (which is NOT
 // 0-based for CTAs of a cluster):
 //   [W0, +256)            mbarriers full[kStages], empty[kStages]
 //   [W0+256, +768)        split-k exchange buffer (same offset in every CTA of the cluster: DSMEM)
-//   [W0+1024, T)          as many 16 KiB ring stages as fit below the table
+//   [W0+1024, T)          as many ring stages as fit below the table
 //   [T, T+64K)            pair table, T = first 64 KiB-aligned address >= W0+1024; entry pitch 256 B:
 //                         even 128 B half-lines = table, odd half-lines = permuted activations
 //   [T+64K, ...)          remaining ring stages, group scale/zero words, reduction scratch
 constexpr uint32_t kCtrlBytes = 1024u;
 constexpr uint32_t kExchOff = 256u;
 constexpr uint32_t kTableBytes = 0x10000u;      // 256 entries * 256 B pitch
-constexpr uint32_t kSzBytes = 32768u;           // staged (scale, zero) words: 256 groups x 32 rows
+constexpr uint32_t kSzBytes = 16384u;           // staged (scale, zero) words: 128 groups x 32 rows
 constexpr uint32_t kRedBytes = kWarps * 4 * 32 * 4;        // [warp][4][32] fp32 reduction scratch
-// worst case over the alignment of W0: control + < 16 KiB unusable + table + all stages + sz + red
+// worst case over the alignment of W0: control + < one stage unusable + table + all stages + sz + red
 constexpr uint32_t kDynSmemBytes = kCtrlBytes + kStageBytes + kTableBytes + kStages * kStageBytes + kSzBytes + kRedBytes;
+static_assert(kDynSmemBytes <= 232448u, "exceeds the 227 KiB opt-in shared memory of sm_100");
 constexpr int kMaxXBytes = 32768;      // capacity of the activation area (odd half-lines of the table)
-constexpr int kPre = 4;                // x items / sz words per thread whose loads are issued before the TMA starts
+constexpr int kPre = 2;                // x items / sz words per thread whose loads are issued before the TMA starts
 
 struct Params {
   const uint8_t* w;      // packed weight
@@ -82,7 +83,7 @@ struct Params {
   int glog2;             // log2(group)
   int64_t tile_stride;   // bytes between consecutive n-tiles of the packed weight = 4 * k
   int64_t y_stride;      // elements between activation rows of y (= total w_rows)
-  int x_row_bytes;       // staged bytes per activation row, multiple of 128
+  int x_row_bytes;       // staged bytes per activation row, multiple of 256 (whole 128-k chunks)
   int splits;            // cluster size along k (gridDim.y)
 };
 
@@ -222,10 +223,71 @@ struct Geo<8> {  // slice = [1 super-tile][32 lanes][4 words]; row g at +g*64
 };
 
 // ---------------------------------------------------------------------------------------
+// Exact per-row fallback, taken only when a CTA produced a non-finite sum.  The block-structured
+// mma operand relies on 0 * w == 0; an Inf/NaN weight (mx4 exponents >= 254, non-finite LUT or
+// scale) breaks that for the rows sharing its mma row.  Recomputing the CTA's rows one at a time
+// (decode -> FFMA, like the tensor core: exact products, fp32 accumulate) confines the non-finite
+// value to the row that owns it, which is what the reference does
+// (tests/tinygemm/test_tinygemm_mx4.py:443-506).  out[mi][row] fp32.
+// ---------------------------------------------------------------------------------------
+template <tg_dtype DT, int IK>
+__device__ __noinline__ void slow_rows(const Params& p, int row0, int rows_valid, int chunk_begin, int chunk_end,
+                                       float* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp >= kWarps) return;
+  const int kb = chunk_begin * kChunkK, ke = min(chunk_end * kChunkK, p.k);
+  const int n_groups = p.k >> p.glog2;
+  constexpr int kWordsPerSuper = 2 * IK;  // words of one row per super-tile (16*IK k)
+  const uint32_t* wq = reinterpret_cast<const uint32_t*>(p.w);
+  for (int rr = warp * 2; rr < warp * 2 + 2; ++rr) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rr < rows_valid && ke > kb) {
+      const int row = row0 + rr;
+      const int64_t tile_words = p.tile_stride / 4;
+      const int ks0 = kb / (16 * IK);
+      const int n_words = (ke - kb) / 8;
+      for (int wn = lane; wn < n_words; wn += 32) {
+        const int ks = ks0 + wn / kWordsPerSuper, rem = wn % kWordsPerSuper;
+        const int q = rem / (IK / 2), j = rem % (IK / 2);
+        const uint32_t w = wq[(int64_t)(row >> 3) * tile_words + ((int64_t)ks * 32 + 4 * (row & 7) + q) * (IK / 2) + j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int kk = (ks * IK + 2 * j + (i >> 2)) * 16 + 2 * q + (i & 1) + ((i >> 1) & 1) * 8;
+          const uint32_t code = (w >> ((i >> 1) * 4 + (i & 1) * 16)) & 0xfu;
+          const int gi = kk >> p.glog2;
+          uint32_t szw;
+          if (p.sz == nullptr) szw = e8m0_to_dt<DT>((uint32_t)p.exps[(int64_t)row * n_groups + gi]) | 0x80000000u;
+          else szw = p.sz[(int64_t)gi * p.w_rows + row];
+          const uint32_t v = p.lut[(int64_t)row * p.lut_stride + code];
+          const uint32_t wd = fma2<DT>(v, szw & 0xffffu, szw >> 16) & 0xffffu;  // low half: the single-rounded FMA
+          float wf;
+          if constexpr (DT == TG_BF16) wf = __uint_as_float(wd << 16);
+          else wf = __half2float(__ushort_as_half((unsigned short)wd));
+          for (int mi = 0; mi < p.m; ++mi) {
+            const uint16_t xv = p.x[(int64_t)mi * p.k + kk];
+            float xf;
+            if constexpr (DT == TG_BF16) xf = __uint_as_float((uint32_t)xv << 16);
+            else xf = __half2float(__ushort_as_half(xv));
+            a[mi] = fmaf(wf, xf, a[mi]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      float v = a[mi];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) out[mi * 32 + rr] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // the kernel
 //   M1 = true : exactly one activation row, weights are the mma A operand (two k-sets)
 //   M1 = false: 1..4 activation rows, weights are the mma B operand
-// grid = (row blocks, splits), cluster = (1, splits, 1); block = 8 consumer warps + 1 producer warp
+// grid = (row blocks, splits), cluster = (1, splits, 1); block = 16 consumer warps + 1 producer warp
 // ---------------------------------------------------------------------------------------
 template <tg_dtype DT, int IK, bool M1>
 __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) {
@@ -240,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   const int rows_valid = min(kRowsPerCta, p.w_rows - row0);  // multiple of 8
   const int tiles_valid = rows_valid >> 3;
 
-  // k range of this CTA in 128-wide chunks; a stage is 8 consecutive chunks (one per consumer warp)
+  // k range of this CTA in 128-wide chunks; a stage is kWarps consecutive chunks (one per consumer warp)
   const int chunks_total = (p.k + kChunkK - 1) / kChunkK;
   const int chunks_per_split = (chunks_total + p.splits - 1) / p.splits;
   const int chunk_begin = split * chunks_per_split;
@@ -266,17 +328,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   const int group_first = (chunk_begin * kChunkK) >> p.glog2;
   const int group_last = chunk_end > chunk_begin ? (min(chunk_end * kChunkK, p.k) - 1) >> p.glog2 : group_first;
   const int n_groups_cta = group_last - group_first + 1;
-  const bool sz_staged = (uint32_t)n_groups_cta * 128u <= kSzBytes;
-  const bool is_mx4 = (p.sz == nullptr);
+  const bool is_mx4 = (p.sz == nullptr);  // the host picks `splits` so that n_groups_cta * 128 <= kSzBytes
 
   // ---- consumers issue their small global loads (LUT row, first activations, first scale/zero words)
   //      BEFORE the bulk weight stream is started, so they are not queued behind it in the memory system
   uint4 lut0 = make_uint4(0, 0, 0, 0), lut1 = lut0;
   uint32_t lut_hi = 0;
   uint32_t px1[kPre], px2[kPre], psz[kPre];
-  const int item_begin = chunk_begin * (kChunkK >> 2);  // one x item = 4 k values of one tile = 8 staged bytes
-  const int item_end = min(chunk_end * (kChunkK >> 2), p.k >> 2);
-  const int sz_words = sz_staged ? n_groups_cta * 32 : 0;
+  // one x item = 4 k values of one tile = 8 staged bytes; items beyond k (tail of the last chunk) are zero
+  const int item_begin = chunk_begin * (kChunkK >> 2);
+  const int item_end = chunk_end * (kChunkK >> 2);
+  const int item_valid_end = p.k >> 2;
+  const int sz_words = n_groups_cta * 32;
   auto load_sz_word = [&](int i) -> uint32_t {  // word i = (group i / 32, row i % 32) of this CTA
     const int gi = group_first + (i >> 5);
     const int row = min(row0 + (i & 31), p.w_rows - 1);
@@ -288,13 +351,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     const uint16_t* lrow = p.lut + (int64_t)row * p.lut_stride;
     lut0 = *reinterpret_cast<const uint4*>(lrow);
     lut1 = *reinterpret_cast<const uint4*>(lrow + 8);
-    lut_hi = *reinterpret_cast<const uint32_t*>(lrow + 2 * warp);  // (T[2w], T[2w+1])
+    lut_hi = (uint32_t)lrow[warp];  // T[w]: this warp builds the 16 table entries whose high nibble is w
     const uint32_t* xr = reinterpret_cast<const uint32_t*>(p.x);   // row 0; further rows are loaded later
 #pragma unroll
     for (int i = 0; i < kPre; ++i) {
       const int it = item_begin + (int)threadIdx.x + i * kConsumerThreads;
       px1[i] = px2[i] = psz[i] = 0u;
-      if (it < item_end) {
+      if (it < min(item_end, item_valid_end)) {
         px1[i] = xr[(it >> 2) * 8 + (it & 3)];
         px2[i] = xr[(it >> 2) * 8 + 4 + (it & 3)];
       }
@@ -333,17 +396,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     }
   } else {
     // =========================== consumers ===========================
-    // ---- pair table: entry e of row L at table_base + e*256 + 4L;  warp w builds e in [32w, 32w+32) ----
+    // ---- pair table: entry e = hi*16 + lo of row L at table_base + e*256 + 4L;  warp w builds hi = w ----
     {
       const uint32_t tp_[8] = {lut0.x, lut0.y, lut0.z, lut0.w, lut1.x, lut1.y, lut1.z, lut1.w};
-      const uint32_t dst = table_base + (uint32_t)(warp * 32) * 256u + 4u * lane;
+      const uint32_t dst = table_base + (uint32_t)(warp * 16) * 256u + 4u * lane;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int lo = 0; lo < 16; ++lo) {
-          const uint32_t sel = (h ? 0x7600u : 0x5400u) | ((lo & 1) ? 0x32u : 0x10u);
-          sts32(dst + (uint32_t)(h * 16 + lo) * 256u, prmt(tp_[lo >> 1], lut_hi, sel));
-        }
+      for (int lo = 0; lo < 16; ++lo) {
+        // result = (T[lo], T[hi]): low half from the LUT pair register, high half = lut_hi's low half
+        sts32(dst + (uint32_t)lo * 256u, prmt(tp_[lo >> 1], lut_hi, (lo & 1) ? 0x5432u : 0x5410u));
       }
     }
 
@@ -352,20 +412,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     //      linear byte offset o of row r lives at x_base + ((r*x_row_bytes + o) / 128) * 256 + (o % 128)
     {
       auto put_x = [&](int r, int it, uint32_t x1, uint32_t x2) {
-        const uint32_t o = (uint32_t)r * p.x_row_bytes + (uint32_t)it * 8u;
+        const uint32_t o = (uint32_t)r * p.x_row_bytes + (uint32_t)(it - item_begin) * 8u;
         sts64(x_base + (o >> 7) * 256u + (o & 127u), prmt(x1, x2, 0x5410u), prmt(x1, x2, 0x7632u));
       };
 #pragma unroll
       for (int i = 0; i < kPre; ++i) {
         const int it = item_begin + (int)threadIdx.x + i * kConsumerThreads;
-        if (it < item_end) put_x(0, it, px1[i], px2[i]);
+        if (it < item_end) put_x(0, it, px1[i], px2[i]);  // zeros beyond k
       }
       for (int r = 0; r < p.m; ++r) {
         const uint32_t* xr = reinterpret_cast<const uint32_t*>(p.x + (int64_t)r * p.k);
         for (int it = item_begin + (int)threadIdx.x + (r == 0 ? kPre * kConsumerThreads : 0); it < item_end;
              it += kConsumerThreads) {
           const int t = it >> 2, pp = it & 3;
-          put_x(r, it, xr[t * 8 + pp], xr[t * 8 + 4 + pp]);
+          const bool ok = it < item_valid_end;
+          put_x(r, it, ok ? xr[t * 8 + pp] : 0u, ok ? xr[t * 8 + 4 + pp] : 0u);
         }
       }
     }
@@ -382,8 +443,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");  // consumers only
 
     // ---- main loop ----
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float accb[4] = {0.f, 0.f, 0.f, 0.f};  // second, independent accumulation chain
+    constexpr int kChains = M1 ? 4 : 2;   // independent HMMA accumulation chains
+    float acc[kChains][4];
+#pragma unroll
+    for (int a = 0; a < kChains; ++a)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[a][i] = 0.f;
     const uint32_t lanebase = table_base | (uint32_t)(lane * 4);
     const int g_ = lane >> 2, q_ = lane & 3;
     // lanes that carry activations in the block-structured operand
@@ -406,58 +471,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
 
     const uint32_t w_lane_off = (uint32_t)(lane >> 3) * kTileStageBytes + (uint32_t)warp * kTileChunkBytes +
                                 (uint32_t)(lane & 7) * Geo<IK>::kRowStride;
-    const int my_row = min(row0 + lane, p.w_rows - 1);
-    const int groups_per_chunk = max(1, kChunkK >> p.glog2);
-
-    // (scale, zero) words of a 128-k chunk: from shared memory when staged, else straight from global one stage
-    // ahead (only for group counts beyond the staging capacity)
-    auto fetch_groups = [&](int c, uint32_t (&raw)[4]) {
-      if (c >= chunk_end) return;
-      const int g0 = (c * kChunkK) >> p.glog2;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        if (t < groups_per_chunk) {
-          const int gi = min(g0 + t, n_groups - 1);
-          if (sz_staged) {
-            raw[t] = lds32(sz_base + (uint32_t)((gi - group_first) * 32 + lane) * 4u);
-          } else if (is_mx4) {
-            raw[t] = e8m0_to_dt<DT>((uint32_t)p.exps[(int64_t)my_row * n_groups + gi]) | 0x80000000u;
-          } else {
-            raw[t] = p.sz[(int64_t)gi * p.w_rows + my_row];
-          }
-        }
-      }
-    };
-
     uint32_t xr0[4] = {0u, 0u, 0u, 0u}, xr1[4] = {0u, 0u, 0u, 0u};  // x fragments (stay zero on inactive lanes)
     uint32_t xs0[4] = {0u, 0u, 0u, 0u}, xs1[4] = {0u, 0u, 0u, 0u};  // rows mi+2 (!M1)
-    uint32_t graw[4] = {0u, 0u, 0u, 0u}, gnext[4] = {0u, 0u, 0u, 0u};
-    fetch_groups(chunk_begin + warp, graw);
 
     for (int j = 0; j < n_stage_iters; ++j) {
       const int s = j % kStages;
       const int c = chunk_begin + j * kWarps + warp;  // this warp's chunk in stage j
-      fetch_groups(c + kWarps, gnext);                // prefetch next stage's scale / zero
-      const int kvalid = c < chunk_end ? min(kChunkK, p.k - c * kChunkK) : 0;
 
-      // group scale / zero for the four tile pairs (32 k each) of this chunk
+      // group (scale, zero) of the four tile pairs (32 k each) of this chunk, from the staged words
       uint32_t s2[4], z2[4];
+      {
+        const int kc = min(c, chunk_end - 1) * kChunkK;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        // group of tile pair t inside the chunk: t (g=32), t/2 (g=64), 0 (g>=128) - no dynamic indexing
-        const uint32_t v = p.glog2 == 5 ? graw[t] : (p.glog2 == 6 ? graw[t >> 1] : graw[0]);
-        s2[t] = prmt(v, v, 0x1010u);  // mx4 words carry zero = -0: fma(v, s, -0) == v * s incl. sign of zero
-        z2[t] = prmt(v, v, 0x3232u);
+        for (int t = 0; t < 4; ++t) {
+          const int gi = ((kc + 32 * t) >> p.glog2) - group_first;
+          const uint32_t v = lds32(sz_base + (uint32_t)(gi * 32 + lane) * 4u);
+          s2[t] = prmt(v, v, 0x1010u);  // mx4 words carry zero = -0: fma(v, s, -0) == v * s incl. sign of zero
+          z2[t] = prmt(v, v, 0x3232u);
+        }
       }
 
       mbar_wait(full_bar + s * 8, (uint32_t)(j / kStages) & 1u);
-      const uint32_t sbase = stage_addr(s) + w_lane_off;
-      // x base for this chunk: tile t0 = 8c + 2tp ; byte offset 32*t0 -> piece (t0/4), within (t0%4)*32
-      const uint32_t xc = x_base + (uint32_t)c * 512u + x_lane_off;
-
+      // A chunk is always processed whole: beyond k the staged activations are zero, so whatever bytes the
+      // stage holds there contribute 0 (finite weights; the non-finite case is handled after the loop).
+      if (c < chunk_end) {
+        const uint32_t sbase = stage_addr(s) + w_lane_off;
+        // x base for this chunk: tile t0 = 8c + 2tp ; byte offset 32*t0 -> piece (t0/4), within (t0%4)*32
+        const uint32_t xc = x_base + (uint32_t)(c - chunk_begin) * 512u + x_lane_off;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (u * 32 < kvalid) {  // warp-uniform tail guard (k % 128 != 0, or no chunk for this warp)
+        for (int u = 0; u < 4; ++u) {
           const uint4 wv = lds128(sbase + Geo<IK>::unit_off(u));
           const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
@@ -480,17 +522,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
             if constexpr (M1) {
               lds64_if(xr0[i], xr1[i], xo, x_active);
               // A = weights: a0/a2 = k-set 1 (tile 2tp), a1/a3 = k-set 2 (tile 2tp+1)
-              mma16816<DT>((i & 1) ? accb : acc, p0, p1, p2, p3, xr0[i], xr1[i]);
+              mma16816<DT>(acc[i], p0, p1, p2, p3, xr0[i], xr1[i]);
             } else {
-              float(&accA)[4] = (i & 1) ? accb : acc;
               lds64_if(xr0[i], xr1[i], xo, xa01);
               lds64_if(xs0[i], xs1[i], xo + x_row2, xa23);
               // tile 2tp: B = (byte0, byte2); A = x (a0,a2 rows mi, a1,a3 rows mi+2)
-              mma16816<DT>(accA, xr0[i], xs0[i], xr1[i], xs1[i], p0, p2);
+              mma16816<DT>(acc[i & 1], xr0[i], xs0[i], xr1[i], xs1[i], p0, p2);
               uint32_t y0 = 0u, y1 = 0u, v0 = 0u, v1 = 0u;
               lds64_if(y0, y1, xo + 32u, xa01);
               lds64_if(v0, v1, xo + 32u + x_row2, xa23);
-              mma16816<DT>(accA, y0, v0, y1, v1, p1, p3);
+              mma16816<DT>(acc[i & 1], y0, v0, y1, v1, p1, p3);
             }
           }
         }
@@ -499,33 +540,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       // hand the stage back to the producer
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar + s * 8) : "memory");
-#pragma unroll
-      for (int t = 0; t < 4; ++t) graw[t] = gnext[t];
     }
 
     // ---- per-warp partial results -> red[warp][j][row] fp32 ----
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] += accb[i];
+    for (int a = 1; a < kChains; ++a)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[0][i] += acc[a][i];
     const uint32_t rbase = red_base + (uint32_t)warp * 512u;
     if constexpr (M1) {
       // valid: lanes q_<2: acc[0],acc[1] = rows 4g+2q_, 4g+2q_+1 (k-set 1); lanes q_>=2: acc[2],acc[3] = rows
       // 4g+2(q_-2), +1 (k-set 2)
       const int jj = q_ >> 1;
       const int r = 4 * g_ + 2 * (q_ & 1);
-      sts32(rbase + (uint32_t)(jj * 32 + r) * 4u, __float_as_uint(jj ? acc[2] : acc[0]));
-      sts32(rbase + (uint32_t)(jj * 32 + r + 1) * 4u, __float_as_uint(jj ? acc[3] : acc[1]));
+      sts32(rbase + (uint32_t)(jj * 32 + r) * 4u, __float_as_uint(jj ? acc[0][2] : acc[0][0]));
+      sts32(rbase + (uint32_t)(jj * 32 + r + 1) * 4u, __float_as_uint(jj ? acc[0][3] : acc[0][1]));
     } else {
       // acc[0],acc[1] = C[g_][2q_, 2q_+1]: mi = g_/4, rows 4*(2q_)+g_%4 and 4*(2q_+1)+g_%4; acc[2],acc[3]: mi + 2
       const int mi = g_ >> 2, qq = g_ & 3;
-      sts32(rbase + (uint32_t)(mi * 32 + 8 * q_ + qq) * 4u, __float_as_uint(acc[0]));
-      sts32(rbase + (uint32_t)(mi * 32 + 8 * q_ + 4 + qq) * 4u, __float_as_uint(acc[1]));
-      sts32(rbase + (uint32_t)((mi + 2) * 32 + 8 * q_ + qq) * 4u, __float_as_uint(acc[2]));
-      sts32(rbase + (uint32_t)((mi + 2) * 32 + 8 * q_ + 4 + qq) * 4u, __float_as_uint(acc[3]));
+      sts32(rbase + (uint32_t)(mi * 32 + 8 * q_ + qq) * 4u, __float_as_uint(acc[0][0]));
+      sts32(rbase + (uint32_t)(mi * 32 + 8 * q_ + 4 + qq) * 4u, __float_as_uint(acc[0][1]));
+      sts32(rbase + (uint32_t)((mi + 2) * 32 + 8 * q_ + qq) * 4u, __float_as_uint(acc[0][2]));
+      sts32(rbase + (uint32_t)((mi + 2) * 32 + 8 * q_ + 4 + qq) * 4u, __float_as_uint(acc[0][3]));
     }
   }
   __syncthreads();
 
-  // ---- CTA-level sums: thread (tj, trow) adds the 8 warps' partials in warp order ----
+  // ---- CTA-level sums: thread (tj, trow) adds the warps' partials in warp order ----
   const int nj = M1 ? 1 : p.m;
   float total = 0.f;
   const int tj = threadIdx.x >> 5, trow = threadIdx.x & 31;
@@ -545,6 +586,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     }
   }
 
+  // non-finite sums (Inf/NaN weights) are recomputed row by row so they stay confined to their row
+  const bool bad = threadIdx.x < 128 && tj < nj && trow < rows_valid && !(fabsf(total) <= 3.0e38f);
+  if (__syncthreads_or(bad ? 1 : 0)) {
+    float* out = reinterpret_cast<float*>(smem_raw + (red_base - dyn_base));
+    slow_rows<DT, IK>(p, row0, rows_valid, chunk_begin, chunk_end, out);
+    __syncthreads();
+    if (threadIdx.x < 128) total = out[tj * 32 + trow];
+  }
+
   if (p.splits == 1) {
     if (threadIdx.x < 128 && tj < nj && trow < rows_valid)
       p.y[(int64_t)tj * p.y_stride + row0 + trow] = f32_to_dt<DT>(total);
@@ -553,7 +603,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
 
   // split-k: every CTA of the cluster publishes its 32 x nj partials; rank 0 adds them in rank order
   cg::cluster_group cluster = cg::this_cluster();
-  __syncthreads();  // everyone is done reading red[] of all warps
   float* part = reinterpret_cast<float*>(smem_raw + kExchOff);
   if (threadIdx.x < 128) part[tj * 32 + trow] = total;
   cluster.sync();
@@ -604,11 +653,7 @@ int launch_one(const Params& p, int row_blocks, cudaStream_t st) {
 template <tg_dtype DT, int IK>
 int launch_m(Params p, int row_blocks, int64_t rows_x, const uint16_t* x, uint16_t* y, cudaStream_t st) {
   // activation rows are processed in passes of up to 4 (bounded by the staging area)
-  const int cap = kMaxXBytes / p.x_row_bytes;
-  if (cap < 1) {
-    set_error("k = %d is too large for the shared-memory activation stage (max %d)", p.k, kMaxXBytes / 2);
-    return TG_ERR_UNSUPPORTED;
-  }
+  const int cap = kMaxXBytes / p.x_row_bytes;  // >= 1 by the choice of `splits`
   const int per_pass = cap < 4 ? cap : 4;
   for (int64_t r0 = 0; r0 < rows_x; r0 += per_pass) {
     p.m = (int)((rows_x - r0) < per_pass ? (rows_x - r0) : per_pass);
@@ -646,7 +691,6 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
   p.glog2 = group == 32 ? 5 : group == 64 ? 6 : group == 128 ? 7 : 8;
   p.tile_stride = 4 * k;
   p.y_stride = w_rows;
-  p.x_row_bytes = (int)((2 * k + 127) / 128 * 128);
 
   if (fmt == TG_W4_ANY4_GLOBAL || fmt == TG_W4_ANY4_ROWWISE) {
     p.lut = reinterpret_cast<const uint16_t*>(lut);
@@ -657,11 +701,24 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
   }
 
   const int row_blocks = (int)div_up(w_rows, kRowsPerCta);
-  // split k across a cluster when the row blocks alone cannot fill the machine
   const int chunks = (int)div_up(k, kChunkK);
+  // k is split across a thread-block cluster (a) when the row blocks alone cannot fill the machine and
+  // (b) as far as needed for one CTA's activations and group words to fit its shared-memory staging areas
   int splits = 1;
-  while (splits < 8 && row_blocks * splits * 2 <= 148 && chunks / (splits * 2) >= 8) splits *= 2;
+  while (splits < 8 && row_blocks * splits * 2 <= 148 && chunks / (splits * 2) >= kWarps) splits *= 2;
+  auto fits = [&](int sp) {
+    const int64_t cps = div_up(chunks, sp);                         // chunks per split
+    const int64_t groups = cps * kChunkK / group + 2;               // groups touched by one split (upper bound)
+    return cps * 256 <= kMaxXBytes && groups * 128 <= (int64_t)kSzBytes;
+  };
+  while (splits < 8 && !fits(splits)) ++splits;
+  if (!fits(splits)) {
+    set_error("k = %lld with group %d exceeds what one cluster can stage (k <= %d at this group size)", (long long)k,
+              group, (int)(8 * (kSzBytes / 128 - 2) * group));
+    return TG_ERR_UNSUPPORTED;
+  }
   p.splits = splits;
+  p.x_row_bytes = (int)(div_up(chunks, splits) * 256);  // one split's activations, whole 128-k chunks
 
   if (dt == TG_BF16)
     return launch_ik<TG_BF16>(p, ik, row_blocks, rows_x, (const uint16_t*)x, (uint16_t*)y, st);

@@ -274,6 +274,10 @@ def run_ours(args):
         torch.cuda.empty_cache()
         return out
 
+    if args.profile_shape:  # ncu helper: just run one shape eagerly, no JSON contract
+        r = bench_shape(args.profile_shape, args.profile_shape, args.steps, args.warmup, False)
+        print(json.dumps(r))
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     head = bench_shape(HEADLINE, HEADLINE, args.steps, args.warmup, True)
     extra = [bench_shape(s, s, max(3, args.steps // 2), args.warmup, False) for s in EXTRA_SHAPES]
@@ -326,6 +330,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--profile-shape", type=int, default=0, help="(for ncu) run only the n=k=N GEMV set")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
