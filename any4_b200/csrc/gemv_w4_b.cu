@@ -67,7 +67,8 @@ constexpr uint32_t kRedBytes = kWarps * 4 * 32 * 4;        // [warp][4][32] fp32
 constexpr uint32_t kDynSmemBytes = kCtrlBytes + kStageBytes + kTableBytes + kStages * kStageBytes + kSzBytes + kRedBytes;
 static_assert(kDynSmemBytes <= 232448u, "exceeds the 227 KiB opt-in shared memory of sm_100");
 constexpr int kMaxXBytes = 32768;      // capacity of the activation area (odd half-lines of the table)
-constexpr int kPre = 2;                // x items / sz words per thread whose loads are issued before the TMA starts
+constexpr int kPre = 8;                // x items / sz words per thread whose loads are issued before the TMA starts
+                                       // (8 x 512 threads covers all of one activation row and all staged group words)
 
 struct Params {
   const uint8_t* w;      // packed weight
@@ -140,11 +141,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// 1-D bulk TMA global -> shared, completion on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
+// 1-D bulk TMA global -> shared, completion on an mbarrier (SASS: UBLKCP).  The weights are read exactly
+// once, so they carry an L2 evict-first policy and leave the small reused tensors (x, LUT, scales) resident.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
+}
+// pull a (16-byte multiple) range into L2 without a destination: used for the NEXT wave's small tensors
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 template <tg_dtype DT>
@@ -380,6 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     // =========================== TMA producer (one elected lane) ===========================
     if (lane == 0) {
       const uint8_t* wsrc = p.w + (int64_t)(rb * 4) * p.tile_stride;
+      const uint64_t pol = l2_evict_first_policy();
       for (int j = 0; j < n_stage_iters; ++j) {
         const int s = j % kStages;
         if (j >= kStages) mbar_wait(empty_bar + s * 8, (uint32_t)(j / kStages - 1) & 1u);
@@ -391,7 +404,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
         mbar_expect_tx(bar, bytes * (uint32_t)tiles_valid);
         const uint32_t dst = stage_addr(s);
         for (int t = 0; t < tiles_valid; ++t)
-          bulk_g2s(dst + t * kTileStageBytes, wsrc + t * p.tile_stride + (int64_t)k0 * 4, bytes, bar);
+          bulk_g2s(dst + t * kTileStageBytes, wsrc + t * p.tile_stride + (int64_t)k0 * 4, bytes, bar, pol);
+      }
+    } else {
+      // lanes 1..31: warm L2 with the LUT rows and group words of the row block one wave ahead, so that
+      // block's prologue does not pay a DRAM round trip behind the weight stream
+      const int nrb = rb + 148;  // one full wave of CTAs ahead
+      const int nrow0 = nrb * kRowsPerCta;
+      if (nrow0 + kRowsPerCta <= p.w_rows) {
+        if (lane == 1 && p.lut_stride) l2_prefetch(p.lut + (int64_t)nrow0 * p.lut_stride, kRowsPerCta * 32);
+        if (!is_mx4)
+          for (int g = group_first + lane - 1; g <= group_last; g += 31)
+            l2_prefetch(p.sz + (int64_t)g * p.w_rows + nrow0, kRowsPerCta * 4);
       }
     }
   } else {
