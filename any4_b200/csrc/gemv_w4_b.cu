@@ -86,6 +86,7 @@ struct Params {
   int64_t y_stride;      // elements between activation rows of y (= total w_rows)
   int x_row_bytes;       // staged bytes per activation row, multiple of 256 (whole 128-k chunks)
   int splits;            // cluster size along k (gridDim.y)
+  unsigned long long* trace;  // optional [CTAs][16] globaltimer stamps (debug, tg_debug_set_trace)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -122,6 +123,14 @@ __device__ __forceinline__ void lds64_if(uint32_t& a, uint32_t& b, uint32_t addr
       : "r"(addr), "r"(p));
 }
 
+// predicated 16-byte shared load into two (b0, b1) pairs
+__device__ __forceinline__ void lds128_if(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, uint32_t addr, uint32_t p) {
+  asm volatile(
+      "{ .reg .pred pp; setp.ne.u32 pp, %5, 0; @pp ld.shared.v4.b32 {%0,%1,%2,%3}, [%4]; }"
+      : "+r"(a), "+r"(b), "+r"(c), "+r"(d)
+      : "r"(addr), "r"(p));
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -154,9 +163,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       "l"(src), "r"(bytes), "r"(bar), "l"(pol)
       : "memory");
 }
-// pull a (16-byte multiple) range into L2 without a destination: used for the NEXT wave's small tensors
-__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+// pull one 128-byte line into L2 (plain LSU prefetch - NOT a bulk-TMA op: small bulk operations would
+// queue in front of the weight stream in the TMA unit); used for the NEXT wave's small tensors
+__device__ __forceinline__ void l2_prefetch_line(const void* src) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+}
+
+__device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
+  if (p.trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = t;
+  }
 }
 
 template <tg_dtype DT>
@@ -218,6 +236,8 @@ struct Geo<4> {  // slice = [2 super-tiles][32 lanes][2 words]; row g at +g*32 i
   __device__ static constexpr int unit_off(int u) { return (u >> 1) * 256 + (u & 1) * 16; }
   __device__ static constexpr int q(int u, int i) { return (u & 1) * 2 + (i >> 1); }
   __device__ static constexpr int tp(int u, int i) { return (u >> 1) * 2 + (i & 1); }
+  // words i and i + 2 use the same tile pair and adjacent k-slots: their activations are 16 contiguous bytes
+  static constexpr int kXPartner = 2;
 };
 template <>
 struct Geo<2> {  // slice = [4 super-tiles][32 lanes][1 word]; row g at +g*16 inside each 128 B
@@ -225,6 +245,7 @@ struct Geo<2> {  // slice = [4 super-tiles][32 lanes][1 word]; row g at +g*16 in
   __device__ static constexpr int unit_off(int u) { return u * 128; }
   __device__ static constexpr int q(int, int i) { return i; }
   __device__ static constexpr int tp(int u, int) { return u; }
+  static constexpr int kXPartner = 1;  // words (0,1) and (2,3) are adjacent k-slots of one tile pair
 };
 template <>
 struct Geo<8> {  // slice = [1 super-tile][32 lanes][4 words]; row g at +g*64
@@ -232,6 +253,7 @@ struct Geo<8> {  // slice = [1 super-tile][32 lanes][4 words]; row g at +g*64
   __device__ static constexpr int unit_off(int u) { return u * 16; }
   __device__ static constexpr int q(int u, int) { return u; }
   __device__ static constexpr int tp(int, int i) { return i; }
+  static constexpr int kXPartner = 0;  // each word is a different tile pair: no 16-byte pairing
 };
 
 // ---------------------------------------------------------------------------------------
@@ -308,6 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) trace_stamp(p, 0);
   const int rb = blockIdx.x;                    // row block
   const int split = blockIdx.y;                 // k split (rank in cluster)
   const int row0 = rb * kRowsPerCta;
@@ -378,44 +401,55 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     }
   }
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar + s * 8, 1);
-      mbar_init(empty_bar + s * 8, kWarps);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-
   if (warp == kWarps) {
-    // =========================== TMA producer (one elected lane) ===========================
+    // =========================== TMA producer warp: starts the weight stream immediately ===========================
+    const uint8_t* wsrc = p.w + (int64_t)(rb * 4) * p.tile_stride;
+    uint64_t pol = 0;
+    auto issue_stage = [&](int j) {
+      const int s = j % kStages;
+      const int c0 = chunk_begin + j * kWarps;
+      const int k0 = c0 * kChunkK;
+      const int kvalid = min(min(kStageK, (chunk_end - c0) * kChunkK), p.k - k0);
+      const uint32_t bytes = (uint32_t)kvalid * 4u;  // per n-tile: 8 rows * kvalid / 2
+      const uint32_t bar = full_bar + s * 8;
+      mbar_expect_tx(bar, bytes * (uint32_t)tiles_valid);
+      const uint32_t dst = stage_addr(s);
+      for (int t = 0; t < tiles_valid; ++t) {
+        // 4 KiB bulk copies: the size class that sustains full HBM rate (scripts/microbench/stream_bw.cu)
+        for (uint32_t o = 0; o < bytes; o += 4096u)
+          bulk_g2s(dst + t * kTileStageBytes + o, wsrc + t * p.tile_stride + (int64_t)k0 * 4 + o, min(4096u, bytes - o),
+                   bar, pol);
+      }
+    };
     if (lane == 0) {
-      const uint8_t* wsrc = p.w + (int64_t)(rb * 4) * p.tile_stride;
-      const uint64_t pol = l2_evict_first_policy();
-      for (int j = 0; j < n_stage_iters; ++j) {
-        const int s = j % kStages;
-        if (j >= kStages) mbar_wait(empty_bar + s * 8, (uint32_t)(j / kStages - 1) & 1u);
-        const int c0 = chunk_begin + j * kWarps;
-        const int k0 = c0 * kChunkK;
-        const int kvalid = min(min(kStageK, (chunk_end - c0) * kChunkK), p.k - k0);
-        const uint32_t bytes = (uint32_t)kvalid * 4u;  // per n-tile: 8 rows * kvalid / 2
-        const uint32_t bar = full_bar + s * 8;
-        mbar_expect_tx(bar, bytes * (uint32_t)tiles_valid);
-        const uint32_t dst = stage_addr(s);
-        for (int t = 0; t < tiles_valid; ++t)
-          bulk_g2s(dst + t * kTileStageBytes, wsrc + t * p.tile_stride + (int64_t)k0 * 4, bytes, bar, pol);
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(full_bar + s * 8, 1);
+        mbar_init(empty_bar + s * 8, kWarps);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      pol = l2_evict_first_policy();
+      trace_stamp(p, 2);
+      for (int j = 0; j < min(n_stage_iters, kStages); ++j) issue_stage(j);
+      trace_stamp(p, 3);
+    }
+    __syncwarp();
+    // tell the consumers the barriers exist (they wait on named barrier 2 before their main loop)
+    asm volatile("bar.arrive 2, %0;" ::"n"(kThreads) : "memory");
+    if (lane == 0) {
+      for (int j = kStages; j < n_stage_iters; ++j) {
+        mbar_wait(empty_bar + (j % kStages) * 8, (uint32_t)(j / kStages - 1) & 1u);
+        issue_stage(j);
       }
     } else {
-      // lanes 1..31: warm L2 with the LUT rows and group words of the row block one wave ahead, so that
+      // lanes 1..31: warm L2 with the LUT rows and group words of the row block one wave of CTAs ahead, so that
       // block's prologue does not pay a DRAM round trip behind the weight stream
-      const int nrb = rb + 148;  // one full wave of CTAs ahead
-      const int nrow0 = nrb * kRowsPerCta;
+      const int nrow0 = (rb + 148) * kRowsPerCta;
       if (nrow0 + kRowsPerCta <= p.w_rows) {
-        if (lane == 1 && p.lut_stride) l2_prefetch(p.lut + (int64_t)nrow0 * p.lut_stride, kRowsPerCta * 32);
+        if (lane <= 8 && p.lut_stride) l2_prefetch_line(p.lut + (int64_t)nrow0 * p.lut_stride + (lane - 1) * 64);
         if (!is_mx4)
           for (int g = group_first + lane - 1; g <= group_last; g += 31)
-            l2_prefetch(p.sz + (int64_t)g * p.w_rows + nrow0, kRowsPerCta * 4);
+            l2_prefetch_line(p.sz + (int64_t)g * p.w_rows + nrow0);
       }
     }
   } else {
@@ -464,7 +498,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       for (int w = (int)threadIdx.x + kPre * kConsumerThreads; w < sz_words; w += kConsumerThreads)
         sts32(sz_base + (uint32_t)w * 4u, load_sz_word(w));
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");  // consumers only
+    if (threadIdx.x == 0) trace_stamp(p, 4);
+    asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");  // 512 consumers + the producer warp's arrive
+    if (threadIdx.x == 0) trace_stamp(p, 5);
 
     // ---- main loop ----
     constexpr int kChains = M1 ? 4 : 2;   // independent HMMA accumulation chains
@@ -516,6 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       }
 
       mbar_wait(full_bar + s * 8, (uint32_t)(j / kStages) & 1u);
+      if (threadIdx.x == 0 && j < 4) trace_stamp(p, 6 + j);
       // A chunk is always processed whole: beyond k the staged activations are zero, so whatever bytes the
       // stage holds there contribute 0 (finite weights; the non-finite case is handled after the loop).
       if (c < chunk_end) {
@@ -526,6 +563,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
         for (int u = 0; u < 4; ++u) {
           const uint4 wv = lds128(sbase + Geo<IK>::unit_off(u));
           const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+          if constexpr (M1) {
+            // activations of the unit's four words: 16-byte loads where two words are adjacent in x
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t xo_i = xc + (uint32_t)((Geo<IK>::tp(u, i) >> 1) * 256 + (Geo<IK>::tp(u, i) & 1) * 64 +
+                                                    Geo<IK>::q(u, i) * 8);
+              constexpr int P = Geo<IK>::kXPartner;
+              if constexpr (P == 0) {
+                lds64_if(xr0[i], xr1[i], xo_i, x_active);
+              } else if ((i % (2 * P)) < P) {
+                lds128_if(xr0[i], xr1[i], xr0[i + P], xr1[i + P], xo_i, x_active);
+              }
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int q = Geo<IK>::q(u, i);
@@ -544,7 +595,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
             // x for tile 2tp, slot q: bytes (tp/2)*256 + (tp%2)*64 + 8q of this chunk's x
             const uint32_t xo = xc + (uint32_t)((tp >> 1) * 256 + (tp & 1) * 64 + q * 8);
             if constexpr (M1) {
-              lds64_if(xr0[i], xr1[i], xo, x_active);
               // A = weights: a0/a2 = k-set 1 (tile 2tp), a1/a3 = k-set 2 (tile 2tp+1)
               mma16816<DT>(acc[i], p0, p1, p2, p3, xr0[i], xr1[i]);
             } else {
@@ -566,6 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar + s * 8) : "memory");
     }
 
+    if (threadIdx.x == 0) trace_stamp(p, 10);
     // ---- per-warp partial results -> red[warp][j][row] fp32 ----
 #pragma unroll
     for (int a = 1; a < kChains; ++a)
@@ -590,6 +641,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   }
   __syncthreads();
 
+  if (threadIdx.x == 0) trace_stamp(p, 11);
   // ---- CTA-level sums: thread (tj, trow) adds the warps' partials in warp order ----
   const int nj = M1 ? 1 : p.m;
   float total = 0.f;
@@ -622,6 +674,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   if (p.splits == 1) {
     if (threadIdx.x < 128 && tj < nj && trow < rows_valid)
       p.y[(int64_t)tj * p.y_stride + row0 + trow] = f32_to_dt<DT>(total);
+    if (threadIdx.x == 0) {
+      trace_stamp(p, 12);
+      if (p.trace != nullptr) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 15] = smid;
+      }
+    }
     return;
   }
 
@@ -640,6 +700,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   }
   cluster.sync();  // keep remote shared memory alive until rank 0 has read it
 }
+
+unsigned long long* g_trace_buf = nullptr;  // set by tg_debug_set_trace (not part of the public header)
 
 template <tg_dtype DT, int IK, bool M1>
 int launch_one(const Params& p, int row_blocks, cudaStream_t st) {
@@ -742,6 +804,7 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
     return TG_ERR_UNSUPPORTED;
   }
   p.splits = splits;
+  p.trace = g_trace_buf;
   p.x_row_bytes = (int)(div_up(chunks, splits) * 256);  // one split's activations, whole 128-k chunks
 
   if (dt == TG_BF16)
@@ -750,3 +813,7 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
 }
 
 }  // namespace tg
+
+// debug hook (scripts/trace_kernel.py): every following B-layout 4-bit launch stamps %globaltimer at its
+// phase boundaries into buf[CTA][16]; pass nullptr to switch it off
+extern "C" void tg_debug_set_trace(void* buf) { tg::g_trace_buf = static_cast<unsigned long long*>(buf); }
