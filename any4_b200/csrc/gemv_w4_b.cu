@@ -430,13 +430,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       pol = l2_evict_first_policy();
       trace_stamp(p, 2);
-      for (int j = 0; j < min(n_stage_iters, kStages); ++j) issue_stage(j);
-      trace_stamp(p, 3);
+      if (n_stage_iters > 0) issue_stage(0);
     }
     __syncwarp();
     // tell the consumers the barriers exist (they wait on named barrier 2 before their main loop)
     asm volatile("bar.arrive 2, %0;" ::"n"(kThreads) : "memory");
     if (lane == 0) {
+      // Pipeline fill: request the first stage alone.  All SMs start together, and with every stage of every
+      // SM in flight at once the memory system serves them interleaved: the first stage then lands only when
+      // (almost) everything has.  Requesting the rest once stage 0 is here gets the consumers going ~1 us
+      // earlier, and they need >1 us for a stage anyway.
+      if (n_stage_iters > 1) mbar_wait(full_bar, 0u);
+      for (int j = 1; j < min(n_stage_iters, kStages); ++j) issue_stage(j);
+      trace_stamp(p, 3);
       for (int j = kStages; j < n_stage_iters; ++j) {
         mbar_wait(empty_bar + (j % kStages) * 8, (uint32_t)(j / kStages - 1) & 1u);
         issue_stage(j);
@@ -542,12 +548,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       uint32_t s2[4], z2[4];
       {
         const int kc = min(c, chunk_end - 1) * kChunkK;
+        if (p.glog2 >= 7) {  // one group covers the whole 128-k chunk
+          const uint32_t v = lds32(sz_base + (uint32_t)(((kc >> p.glog2) - group_first) * 32 + lane) * 4u);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int gi = ((kc + 32 * t) >> p.glog2) - group_first;
-          const uint32_t v = lds32(sz_base + (uint32_t)(gi * 32 + lane) * 4u);
-          s2[t] = prmt(v, v, 0x1010u);  // mx4 words carry zero = -0: fma(v, s, -0) == v * s incl. sign of zero
-          z2[t] = prmt(v, v, 0x3232u);
+          for (int t = 0; t < 4; ++t) {
+            s2[t] = prmt(v, v, 0x1010u);  // mx4 words carry zero = -0: fma(v, s, -0) == v * s incl. sign of zero
+            z2[t] = prmt(v, v, 0x3232u);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int gi = ((kc + 32 * t) >> p.glog2) - group_first;
+            const uint32_t v = lds32(sz_base + (uint32_t)(gi * 32 + lane) * 4u);
+            s2[t] = prmt(v, v, 0x1010u);
+            z2[t] = prmt(v, v, 0x3232u);
+          }
         }
       }
 
