@@ -67,7 +67,8 @@ constexpr uint32_t kRedBytes = kWarps * 4 * 32 * 4;        // [warp][4][32] fp32
 constexpr uint32_t kDynSmemBytes = kCtrlBytes + kStageBytes + kTableBytes + kStages * kStageBytes + kSzBytes + kRedBytes;
 static_assert(kDynSmemBytes <= 232448u, "exceeds the 227 KiB opt-in shared memory of sm_100");
 constexpr int kMaxXBytes = 32768;      // capacity of the activation area (odd half-lines of the table)
-constexpr int kPre = 8;                // x items / sz words per thread whose loads are issued before the TMA starts
+constexpr int kPreSz = 4;              // group words per thread prefetched into registers for the next row block
+constexpr int kPre = 8;                // x items per thread whose loads are issued before the TMA starts
                                        // (8 x 512 threads covers all of one activation row and all staged group words)
 
 struct Params {
@@ -321,7 +322,11 @@ __device__ __noinline__ void slow_rows(const Params& p, int row0, int rows_valid
 // the kernel
 //   M1 = true : exactly one activation row, weights are the mma A operand (two k-sets)
 //   M1 = false: 1..4 activation rows, weights are the mma B operand
-// grid = (row blocks, splits), cluster = (1, splits, 1); block = 16 consumer warps + 1 producer warp
+// grid = (G, splits), cluster = (1, splits, 1); block = 16 consumer warps + 1 producer warp.
+// PERSISTENT over row blocks: CTA (s, y) handles row blocks s, s+G, s+2G, ... for its k split y.  The
+// activations are staged once; the producer streams the weights of consecutive row blocks back to back
+// through one ring, so a block's table / scale staging and the previous block's epilogue hide under the
+// stream instead of costing a full kernel prologue + pipeline fill per 32 rows.
 // ---------------------------------------------------------------------------------------
 template <tg_dtype DT, int IK, bool M1>
 __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) {
@@ -331,11 +336,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) trace_stamp(p, 0);
-  const int rb = blockIdx.x;                    // row block
   const int split = blockIdx.y;                 // k split (rank in cluster)
-  const int row0 = rb * kRowsPerCta;
-  const int rows_valid = min(kRowsPerCta, p.w_rows - row0);  // multiple of 8
-  const int tiles_valid = rows_valid >> 3;
+  const int G = (int)gridDim.x;
+  const int row_blocks = (p.w_rows + kRowsPerCta - 1) / kRowsPerCta;
+  const int n_blk = (row_blocks - (int)blockIdx.x + G - 1) / G;   // row blocks of this CTA (>= 1)
 
   // k range of this CTA in 128-wide chunks; a stage is kWarps consecutive chunks (one per consumer warp)
   const int chunks_total = (p.k + kChunkK - 1) / kChunkK;
@@ -359,54 +363,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     return s < n_low ? low_base + (uint32_t)s * kStageBytes : high_base + (uint32_t)(s - n_low) * kStageBytes;
   };
 
-  // group scale/zero of this CTA's k range are staged in shared memory when they fit
+  // group scale/zero words of this CTA's k range (the host picks `splits` so that they fit kSzBytes)
   const int group_first = (chunk_begin * kChunkK) >> p.glog2;
   const int group_last = chunk_end > chunk_begin ? (min(chunk_end * kChunkK, p.k) - 1) >> p.glog2 : group_first;
   const int n_groups_cta = group_last - group_first + 1;
-  const bool is_mx4 = (p.sz == nullptr);  // the host picks `splits` so that n_groups_cta * 128 <= kSzBytes
-
-  // ---- consumers issue their small global loads (LUT row, first activations, first scale/zero words)
-  //      BEFORE the bulk weight stream is started, so they are not queued behind it in the memory system
-  uint4 lut0 = make_uint4(0, 0, 0, 0), lut1 = lut0;
-  uint32_t lut_hi = 0;
-  uint32_t px1[kPre], px2[kPre], psz[kPre];
-  // one x item = 4 k values of one tile = 8 staged bytes; items beyond k (tail of the last chunk) are zero
-  const int item_begin = chunk_begin * (kChunkK >> 2);
-  const int item_end = chunk_end * (kChunkK >> 2);
-  const int item_valid_end = p.k >> 2;
   const int sz_words = n_groups_cta * 32;
-  auto load_sz_word = [&](int i) -> uint32_t {  // word i = (group i / 32, row i % 32) of this CTA
-    const int gi = group_first + (i >> 5);
-    const int row = min(row0 + (i & 31), p.w_rows - 1);
-    if (is_mx4) return e8m0_to_dt<DT>((uint32_t)p.exps[(int64_t)row * n_groups + gi]) | 0x80000000u;  // zero = -0
-    return p.sz[(int64_t)gi * p.w_rows + row];
-  };
-  if (warp < kWarps) {
-    const int row = min(row0 + lane, p.w_rows - 1);
-    const uint16_t* lrow = p.lut + (int64_t)row * p.lut_stride;
-    lut0 = *reinterpret_cast<const uint4*>(lrow);
-    lut1 = *reinterpret_cast<const uint4*>(lrow + 8);
-    lut_hi = (uint32_t)lrow[warp];  // T[w]: this warp builds the 16 table entries whose high nibble is w
-    const uint32_t* xr = reinterpret_cast<const uint32_t*>(p.x);   // row 0; further rows are loaded later
-#pragma unroll
-    for (int i = 0; i < kPre; ++i) {
-      const int it = item_begin + (int)threadIdx.x + i * kConsumerThreads;
-      px1[i] = px2[i] = psz[i] = 0u;
-      if (it < min(item_end, item_valid_end)) {
-        px1[i] = xr[(it >> 2) * 8 + (it & 3)];
-        px2[i] = xr[(it >> 2) * 8 + 4 + (it & 3)];
-      }
-      const int w = (int)threadIdx.x + i * kConsumerThreads;
-      if (w < sz_words) psz[i] = load_sz_word(w);
-    }
-  }
+  const bool is_mx4 = (p.sz == nullptr);
 
   if (warp == kWarps) {
     // =========================== TMA producer warp: starts the weight stream immediately ===========================
-    const uint8_t* wsrc = p.w + (int64_t)(rb * 4) * p.tile_stride;
     uint64_t pol = 0;
-    auto issue_stage = [&](int j) {
-      const int s = j % kStages;
+    auto issue_stage = [&](int rb, int j, int jj) {
+      const int s = jj % kStages;
+      const int tiles_valid = min(kRowsPerCta, p.w_rows - rb * kRowsPerCta) >> 3;
+      const uint8_t* wsrc = p.w + (int64_t)(rb * 4) * p.tile_stride;
       const int c0 = chunk_begin + j * kWarps;
       const int k0 = c0 * kChunkK;
       const int kvalid = min(min(kStageK, (chunk_end - c0) * kChunkK), p.k - k0);
@@ -430,28 +400,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       pol = l2_evict_first_policy();
       trace_stamp(p, 2);
-      if (n_stage_iters > 0) issue_stage(0);
+      if (n_stage_iters > 0) issue_stage((int)blockIdx.x, 0, 0);
     }
     __syncwarp();
     // tell the consumers the barriers exist (they wait on named barrier 2 before their main loop)
     asm volatile("bar.arrive 2, %0;" ::"n"(kThreads) : "memory");
     if (lane == 0) {
-      // Pipeline fill: request the first stage alone.  All SMs start together, and with every stage of every
-      // SM in flight at once the memory system serves them interleaved: the first stage then lands only when
-      // (almost) everything has.  Requesting the rest once stage 0 is here gets the consumers going ~1 us
-      // earlier, and they need >1 us for a stage anyway.
-      if (n_stage_iters > 1) mbar_wait(full_bar, 0u);
-      for (int j = 1; j < min(n_stage_iters, kStages); ++j) issue_stage(j);
-      trace_stamp(p, 3);
-      for (int j = kStages; j < n_stage_iters; ++j) {
-        mbar_wait(empty_bar + (j % kStages) * 8, (uint32_t)(j / kStages - 1) & 1u);
-        issue_stage(j);
+      int jj = 0;
+      for (int b = 0; b < n_blk; ++b) {
+        const int rb = (int)blockIdx.x + b * G;
+        for (int j = 0; j < n_stage_iters; ++j, ++jj) {
+          if (jj == 0) continue;  // issued above
+          // Pipeline fill: the first stage is requested alone.  All SMs start together, and with every stage of
+          // every SM in flight at once the memory system serves them interleaved: the first stage then lands
+          // only when (almost) everything has.  Requesting the rest once stage 0 is here gets the consumers
+          // going ~1 us earlier, and they need > 1 us for a stage anyway.
+          if (jj == 1) {
+            mbar_wait(full_bar, 0u);
+            trace_stamp(p, 3);
+          }
+          if (jj >= kStages) mbar_wait(empty_bar + (jj % kStages) * 8, (uint32_t)(jj / kStages - 1) & 1u);
+          issue_stage(rb, j, jj);
+        }
       }
     } else {
-      // lanes 1..31: warm L2 with the LUT rows and group words of the row block one wave of CTAs ahead, so that
-      // block's prologue does not pay a DRAM round trip behind the weight stream
-      const int nrow0 = (rb + 148) * kRowsPerCta;
-      if (nrow0 + kRowsPerCta <= p.w_rows) {
+      // lanes 1..31: warm L2 with the LUT rows and group words of this CTA's LATER row blocks (plain LSU
+      // prefetches), so their staging does not pay a DRAM round trip behind the weight stream
+      for (int b = 1; b < n_blk; ++b) {
+        const int nrow0 = ((int)blockIdx.x + b * G) * kRowsPerCta;
+        if (nrow0 + kRowsPerCta > p.w_rows) break;
         if (lane <= 8 && p.lut_stride) l2_prefetch_line(p.lut + (int64_t)nrow0 * p.lut_stride + (lane - 1) * 64);
         if (!is_mx4)
           for (int g = group_first + lane - 1; g <= group_last; g += 31)
@@ -460,8 +437,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     }
   } else {
     // =========================== consumers ===========================
-    // ---- pair table: entry e = hi*16 + lo of row L at table_base + e*256 + 4L;  warp w builds hi = w ----
-    {
+    // small per-row-block tensors travel global -> registers -> shared memory; the loads for block b+1 are
+    // issued during the last stage of block b
+    uint4 lut0 = make_uint4(0, 0, 0, 0), lut1 = lut0;
+    uint32_t lut_hi = 0;
+    uint32_t psz[kPreSz];
+    auto load_sz_word = [&](int row0, int i) -> uint32_t {  // word i = (group i / 32, row i % 32) of a row block
+      const int gi = group_first + (i >> 5);
+      const int row = min(row0 + (i & 31), p.w_rows - 1);
+      if (is_mx4) return e8m0_to_dt<DT>((uint32_t)p.exps[(int64_t)row * n_groups + gi]) | 0x80000000u;  // zero = -0
+      return p.sz[(int64_t)gi * p.w_rows + row];
+    };
+    auto load_block_regs = [&](int rb) {
+      const int row0 = rb * kRowsPerCta;
+      const int row = min(row0 + lane, p.w_rows - 1);
+      const uint16_t* lrow = p.lut + (int64_t)row * p.lut_stride;
+      lut0 = *reinterpret_cast<const uint4*>(lrow);
+      lut1 = *reinterpret_cast<const uint4*>(lrow + 8);
+      lut_hi = (uint32_t)lrow[warp];  // T[w]: this warp builds the 16 table entries whose high nibble is w
+#pragma unroll
+      for (int i = 0; i < kPreSz; ++i) {
+        const int w = (int)threadIdx.x + i * kConsumerThreads;
+        psz[i] = w < sz_words ? load_sz_word(row0, w) : 0u;
+      }
+    };
+    // pair table: entry e = hi*16 + lo of row L at table_base + e*256 + 4L;  warp w builds hi = w.
+    // group words: sz_s[group - group_first][row]
+    auto store_block_smem = [&](int rb) {
       const uint32_t tp_[8] = {lut0.x, lut0.y, lut0.z, lut0.w, lut1.x, lut1.y, lut1.z, lut1.w};
       const uint32_t dst = table_base + (uint32_t)(warp * 16) * 256u + 4u * lane;
 #pragma unroll
@@ -469,12 +471,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
         // result = (T[lo], T[hi]): low half from the LUT pair register, high half = lut_hi's low half
         sts32(dst + (uint32_t)lo * 256u, prmt(tp_[lo >> 1], lut_hi, (lo & 1) ? 0x5432u : 0x5410u));
       }
-    }
+#pragma unroll
+      for (int i = 0; i < kPreSz; ++i) {
+        const int w = (int)threadIdx.x + i * kConsumerThreads;
+        if (w < sz_words) sts32(sz_base + (uint32_t)w * 4u, psz[i]);
+      }
+      for (int w = (int)threadIdx.x + kPreSz * kConsumerThreads; w < sz_words; w += kConsumerThreads)
+        sts32(sz_base + (uint32_t)w * 4u, load_sz_word(rb * kRowsPerCta, w));
+    };
 
-    // ---- activations, permuted so that (x[16t+i], x[16t+i+8]) are adjacent:
-    //      xp[16t + 2i] = x[16t + i], xp[16t + 2i + 1] = x[16t + i + 8], i = 0..7
-    //      linear byte offset o of row r lives at x_base + ((r*x_row_bytes + o) / 128) * 256 + (o % 128)
+    // ---- kernel prologue: issue the small global loads first (first block's LUT / group words, activations)
+    load_block_regs((int)blockIdx.x);
+    // one x item = 4 k values of one tile = 8 staged bytes; items beyond k (tail of the last chunk) are zero
+    const int item_begin = chunk_begin * (kChunkK >> 2);
+    const int item_end = chunk_end * (kChunkK >> 2);
+    const int item_valid_end = p.k >> 2;
     {
+      // activations, permuted so that (x[16t+i], x[16t+i+8]) are adjacent:
+      //   xp[16t + 2i] = x[16t + i], xp[16t + 2i + 1] = x[16t + i + 8], i = 0..7
+      // linear byte offset o of row r lives at x_base + ((r*x_row_bytes + o) / 128) * 256 + (o % 128)
+      uint32_t px1[kPre], px2[kPre];
+      const uint32_t* xr0p = reinterpret_cast<const uint32_t*>(p.x);
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) {
+        const int it = item_begin + (int)threadIdx.x + i * kConsumerThreads;
+        px1[i] = px2[i] = 0u;
+        if (it < min(item_end, item_valid_end)) {
+          px1[i] = xr0p[(it >> 2) * 8 + (it & 3)];
+          px2[i] = xr0p[(it >> 2) * 8 + 4 + (it & 3)];
+        }
+      }
       auto put_x = [&](int r, int it, uint32_t x1, uint32_t x2) {
         const uint32_t o = (uint32_t)r * p.x_row_bytes + (uint32_t)(it - item_begin) * 8u;
         sts64(x_base + (o >> 7) * 256u + (o & 127u), prmt(x1, x2, 0x5410u), prmt(x1, x2, 0x7632u));
@@ -494,27 +520,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
         }
       }
     }
-    // ---- group (scale, zero) words: sz_s[group - group_first][row] ----
-    {
-#pragma unroll
-      for (int i = 0; i < kPre; ++i) {
-        const int w = (int)threadIdx.x + i * kConsumerThreads;
-        if (w < sz_words) sts32(sz_base + (uint32_t)w * 4u, psz[i]);
-      }
-      for (int w = (int)threadIdx.x + kPre * kConsumerThreads; w < sz_words; w += kConsumerThreads)
-        sts32(sz_base + (uint32_t)w * 4u, load_sz_word(w));
-    }
+    store_block_smem((int)blockIdx.x);
     if (threadIdx.x == 0) trace_stamp(p, 4);
     asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");  // 512 consumers + the producer warp's arrive
     if (threadIdx.x == 0) trace_stamp(p, 5);
 
-    // ---- main loop ----
-    constexpr int kChains = M1 ? 4 : 2;   // independent HMMA accumulation chains
-    float acc[kChains][4];
-#pragma unroll
-    for (int a = 0; a < kChains; ++a)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[a][i] = 0.f;
+    // ---- loop-invariant lane state ----
     const uint32_t lanebase = table_base | (uint32_t)(lane * 4);
     const int g_ = lane >> 2, q_ = lane & 3;
     // lanes that carry activations in the block-structured operand
@@ -534,186 +545,215 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     const bool has_row23 = M1 ? false : (set1 ? p.m > 2 : p.m > 3);
     const uint32_t xa01 = (x_active && has_row01) ? 1u : 0u;
     const uint32_t xa23 = (x_active && has_row23) ? 1u : 0u;
-
     const uint32_t w_lane_off = (uint32_t)(lane >> 3) * kTileStageBytes + (uint32_t)warp * kTileChunkBytes +
                                 (uint32_t)(lane & 7) * Geo<IK>::kRowStride;
     uint32_t xr0[4] = {0u, 0u, 0u, 0u}, xr1[4] = {0u, 0u, 0u, 0u};  // x fragments (stay zero on inactive lanes)
     uint32_t xs0[4] = {0u, 0u, 0u, 0u}, xs1[4] = {0u, 0u, 0u, 0u};  // rows mi+2 (!M1)
+    constexpr int kChains = 2;            // independent HMMA accumulation chains
+    const int nj = M1 ? 1 : p.m;
+    const int tj = threadIdx.x >> 5, trow = threadIdx.x & 31;
+    float* const exch = reinterpret_cast<float*>(smem_raw + kExchOff);
 
-    for (int j = 0; j < n_stage_iters; ++j) {
-      const int s = j % kStages;
-      const int c = chunk_begin + j * kWarps + warp;  // this warp's chunk in stage j
+    int jj = 0;  // stage counter across row blocks (ring position / parity)
+    for (int b = 0; b < n_blk; ++b) {
+      const int rb = (int)blockIdx.x + b * G;
+      const int row0 = rb * kRowsPerCta;
+      const int rows_valid = min(kRowsPerCta, p.w_rows - row0);  // multiple of 8
+      float acc[kChains][4];
+#pragma unroll
+      for (int a = 0; a < kChains; ++a)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[a][i] = 0.f;
 
-      // group (scale, zero) of the four tile pairs (32 k each) of this chunk, from the staged words
-      uint32_t s2[4], z2[4];
-      {
-        const int kc = min(c, chunk_end - 1) * kChunkK;
-        if (p.glog2 >= 7) {  // one group covers the whole 128-k chunk
-          const uint32_t v = lds32(sz_base + (uint32_t)(((kc >> p.glog2) - group_first) * 32 + lane) * 4u);
+      for (int j = 0; j < n_stage_iters; ++j, ++jj) {
+        const int s = jj % kStages;
+        const int c = chunk_begin + j * kWarps + warp;  // this warp's chunk in stage j
+        if (j == n_stage_iters - 1 && b + 1 < n_blk) load_block_regs(rb + G);  // next block's LUT / group words
+
+        // group (scale, zero) of the four tile pairs (32 k each) of this chunk, from the staged words
+        uint32_t s2[4], z2[4];
+        {
+          const int kc = min(c, chunk_end - 1) * kChunkK;
+          if (p.glog2 >= 7) {  // one group covers the whole 128-k chunk
+            const uint32_t v = lds32(sz_base + (uint32_t)(((kc >> p.glog2) - group_first) * 32 + lane) * 4u);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            s2[t] = prmt(v, v, 0x1010u);  // mx4 words carry zero = -0: fma(v, s, -0) == v * s incl. sign of zero
-            z2[t] = prmt(v, v, 0x3232u);
-          }
-        } else {
+            for (int t = 0; t < 4; ++t) {
+              s2[t] = prmt(v, v, 0x1010u);  // mx4 words carry zero = -0: fma(v, s, -0) == v * s incl. sign of zero
+              z2[t] = prmt(v, v, 0x3232u);
+            }
+          } else {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int gi = ((kc + 32 * t) >> p.glog2) - group_first;
-            const uint32_t v = lds32(sz_base + (uint32_t)(gi * 32 + lane) * 4u);
-            s2[t] = prmt(v, v, 0x1010u);
-            z2[t] = prmt(v, v, 0x3232u);
+            for (int t = 0; t < 4; ++t) {
+              const int gi = ((kc + 32 * t) >> p.glog2) - group_first;
+              const uint32_t v = lds32(sz_base + (uint32_t)(gi * 32 + lane) * 4u);
+              s2[t] = prmt(v, v, 0x1010u);
+              z2[t] = prmt(v, v, 0x3232u);
+            }
           }
         }
-      }
 
-      mbar_wait(full_bar + s * 8, (uint32_t)(j / kStages) & 1u);
-      if (threadIdx.x == 0 && j < 4) trace_stamp(p, 6 + j);
-      // A chunk is always processed whole: beyond k the staged activations are zero, so whatever bytes the
-      // stage holds there contribute 0 (finite weights; the non-finite case is handled after the loop).
-      if (c < chunk_end) {
-        const uint32_t sbase = stage_addr(s) + w_lane_off;
-        // x base for this chunk: tile t0 = 8c + 2tp ; byte offset 32*t0 -> piece (t0/4), within (t0%4)*32
-        const uint32_t xc = x_base + (uint32_t)(c - chunk_begin) * 512u + x_lane_off;
+        mbar_wait(full_bar + s * 8, (uint32_t)(jj / kStages) & 1u);
+        if (threadIdx.x == 0 && jj < 4) trace_stamp(p, 6 + jj);
+        // A chunk is always processed whole: beyond k the staged activations are zero, so whatever bytes the
+        // stage holds there contribute 0 (finite weights; the non-finite case is handled after the loop).
+        if (c < chunk_end) {
+          const uint32_t sbase = stage_addr(s) + w_lane_off;
+          // x base for this chunk: tile t0 = 8c + 2tp ; byte offset 32*t0 -> piece (t0/4), within (t0%4)*32
+          const uint32_t xc = x_base + (uint32_t)(c - chunk_begin) * 512u + x_lane_off;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint4 wv = lds128(sbase + Geo<IK>::unit_off(u));
-          const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-          if constexpr (M1) {
-            // activations of the unit's four words: 16-byte loads where two words are adjacent in x
+          for (int u = 0; u < 4; ++u) {
+            const uint4 wv = lds128(sbase + Geo<IK>::unit_off(u));
+            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+            if constexpr (M1) {
+              // activations of the unit's four words: 16-byte loads where two words are adjacent in x
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t xo_i = xc + (uint32_t)((Geo<IK>::tp(u, i) >> 1) * 256 + (Geo<IK>::tp(u, i) & 1) * 64 +
+                                                      Geo<IK>::q(u, i) * 8);
+                constexpr int P = Geo<IK>::kXPartner;
+                if constexpr (P == 0) {
+                  lds64_if(xr0[i], xr1[i], xo_i, x_active);
+                } else if ((i % (2 * P)) < P) {
+                  lds128_if(xr0[i], xr1[i], xr0[i + P], xr1[i + P], xo_i, x_active);
+                }
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const uint32_t xo_i = xc + (uint32_t)((Geo<IK>::tp(u, i) >> 1) * 256 + (Geo<IK>::tp(u, i) & 1) * 64 +
-                                                    Geo<IK>::q(u, i) * 8);
-              constexpr int P = Geo<IK>::kXPartner;
-              if constexpr (P == 0) {
-                lds64_if(xr0[i], xr1[i], xo_i, x_active);
-              } else if ((i % (2 * P)) < P) {
-                lds128_if(xr0[i], xr1[i], xr0[i + P], xr1[i + P], xo_i, x_active);
+              const int q = Geo<IK>::q(u, i);
+              const int tp = Geo<IK>::tp(u, i);
+              const uint32_t w = ww[i];
+              // byte0: tile 2tp (k0, k0+8)   byte2: tile 2tp (k0+1, k0+9)
+              // byte1: tile 2tp+1 (k0, k0+8) byte3: tile 2tp+1 (k0+1, k0+9)
+              uint32_t p0 = lds32(prmt(w, lanebase, 0x7604u));
+              uint32_t p1 = lds32(prmt(w, lanebase, 0x7614u));
+              uint32_t p2 = lds32(prmt(w, lanebase, 0x7624u));
+              uint32_t p3 = lds32(prmt(w, lanebase, 0x7634u));
+              p0 = fma2<DT>(p0, s2[tp], z2[tp]);
+              p1 = fma2<DT>(p1, s2[tp], z2[tp]);
+              p2 = fma2<DT>(p2, s2[tp], z2[tp]);
+              p3 = fma2<DT>(p3, s2[tp], z2[tp]);
+              // x for tile 2tp, slot q: bytes (tp/2)*256 + (tp%2)*64 + 8q of this chunk's x
+              const uint32_t xo = xc + (uint32_t)((tp >> 1) * 256 + (tp & 1) * 64 + q * 8);
+              if constexpr (M1) {
+                // A = weights: a0/a2 = k-set 1 (tile 2tp), a1/a3 = k-set 2 (tile 2tp+1)
+                mma16816<DT>(acc[i & 1], p0, p1, p2, p3, xr0[i], xr1[i]);
+              } else {
+                lds64_if(xr0[i], xr1[i], xo, xa01);
+                lds64_if(xs0[i], xs1[i], xo + x_row2, xa23);
+                // tile 2tp: B = (byte0, byte2); A = x (a0,a2 rows mi, a1,a3 rows mi+2)
+                mma16816<DT>(acc[i & 1], xr0[i], xs0[i], xr1[i], xs1[i], p0, p2);
+                uint32_t y0 = 0u, y1 = 0u, v0 = 0u, v1 = 0u;
+                lds64_if(y0, y1, xo + 32u, xa01);
+                lds64_if(v0, v1, xo + 32u + x_row2, xa23);
+                mma16816<DT>(acc[i & 1], y0, v0, y1, v1, p1, p3);
               }
             }
           }
+        }
+
+        // hand the stage back to the producer
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar + s * 8) : "memory");
+      }
+      if (threadIdx.x == 0 && b == 0) trace_stamp(p, 10);
+
+      // ---- per-warp partial results -> red[warp][j][row] fp32 ----
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int q = Geo<IK>::q(u, i);
-            const int tp = Geo<IK>::tp(u, i);
-            const uint32_t w = ww[i];
-            // byte0: tile 2tp (k0, k0+8)   byte2: tile 2tp (k0+1, k0+9)
-            // byte1: tile 2tp+1 (k0, k0+8) byte3: tile 2tp+1 (k0+1, k0+9)
-            uint32_t p0 = lds32(prmt(w, lanebase, 0x7604u));
-            uint32_t p1 = lds32(prmt(w, lanebase, 0x7614u));
-            uint32_t p2 = lds32(prmt(w, lanebase, 0x7624u));
-            uint32_t p3 = lds32(prmt(w, lanebase, 0x7634u));
-            p0 = fma2<DT>(p0, s2[tp], z2[tp]);
-            p1 = fma2<DT>(p1, s2[tp], z2[tp]);
-            p2 = fma2<DT>(p2, s2[tp], z2[tp]);
-            p3 = fma2<DT>(p3, s2[tp], z2[tp]);
-            // x for tile 2tp, slot q: bytes (tp/2)*256 + (tp%2)*64 + 8q of this chunk's x
-            const uint32_t xo = xc + (uint32_t)((tp >> 1) * 256 + (tp & 1) * 64 + q * 8);
-            if constexpr (M1) {
-              // A = weights: a0/a2 = k-set 1 (tile 2tp), a1/a3 = k-set 2 (tile 2tp+1)
-              mma16816<DT>(acc[i], p0, p1, p2, p3, xr0[i], xr1[i]);
-            } else {
-              lds64_if(xr0[i], xr1[i], xo, xa01);
-              lds64_if(xs0[i], xs1[i], xo + x_row2, xa23);
-              // tile 2tp: B = (byte0, byte2); A = x (a0,a2 rows mi, a1,a3 rows mi+2)
-              mma16816<DT>(acc[i & 1], xr0[i], xs0[i], xr1[i], xs1[i], p0, p2);
-              uint32_t y0 = 0u, y1 = 0u, v0 = 0u, v1 = 0u;
-              lds64_if(y0, y1, xo + 32u, xa01);
-              lds64_if(v0, v1, xo + 32u + x_row2, xa23);
-              mma16816<DT>(acc[i & 1], y0, v0, y1, v1, p1, p3);
+      for (int a = 1; a < kChains; ++a)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[0][i] += acc[a][i];
+      const uint32_t rbase = red_base + (uint32_t)warp * 512u;
+      if constexpr (M1) {
+        // valid: lanes q_<2: acc[0],acc[1] = rows 4g+2q_, 4g+2q_+1 (k-set 1); lanes q_>=2: acc[2],acc[3] = rows
+        // 4g+2(q_-2), +1 (k-set 2)
+        const int jq = q_ >> 1;
+        const int r = 4 * g_ + 2 * (q_ & 1);
+        sts32(rbase + (uint32_t)(jq * 32 + r) * 4u, __float_as_uint(jq ? acc[0][2] : acc[0][0]));
+        sts32(rbase + (uint32_t)(jq * 32 + r + 1) * 4u, __float_as_uint(jq ? acc[0][3] : acc[0][1]));
+      } else {
+        // acc[0],acc[1] = C[g_][2q_, 2q_+1]: mi = g_/4, rows 4*(2q_)+g_%4 and 4*(2q_+1)+g_%4; acc[2],acc[3]: mi + 2
+        const int mi = g_ >> 2, qq = g_ & 3;
+        sts32(rbase + (uint32_t)(mi * 32 + 8 * q_ + qq) * 4u, __float_as_uint(acc[0][0]));
+        sts32(rbase + (uint32_t)(mi * 32 + 8 * q_ + 4 + qq) * 4u, __float_as_uint(acc[0][1]));
+        sts32(rbase + (uint32_t)((mi + 2) * 32 + 8 * q_ + qq) * 4u, __float_as_uint(acc[0][2]));
+        sts32(rbase + (uint32_t)((mi + 2) * 32 + 8 * q_ + 4 + qq) * 4u, __float_as_uint(acc[0][3]));
+      }
+      // all warps are done with this block's table / group words, and all partials are visible
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+
+      // ---- block sums: thread (tj, trow) adds the warps' partials in warp order ----
+      float total = 0.f;
+      if (threadIdx.x < 128) {
+        if constexpr (M1) {
+          if (tj == 0) {
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+              total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)trow * 4u));
+              total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)(32 + trow) * 4u));
             }
           }
+        } else {
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w)
+            total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)(tj * 32 + trow) * 4u));
         }
       }
+      // next block's table and group words (their loads were issued during the last stage)
+      if (b + 1 < n_blk) store_block_smem(rb + G);
 
-      // hand the stage back to the producer
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar + s * 8) : "memory");
-    }
+      // non-finite sums (Inf/NaN weights) are recomputed row by row so they stay confined to their row;
+      // the vote doubles as the barrier that publishes the next block's table
+      const bool bad = threadIdx.x < 128 && tj < nj && trow < rows_valid && !(fabsf(total) <= 3.0e38f);
+      uint32_t any_bad;
+      asm volatile(
+          "{ .reg .pred pi, po; setp.ne.u32 pi, %1, 0; barrier.cta.red.or.pred.aligned po, 1, %2, pi; selp.u32 %0, 1, 0, po; }"
+          : "=r"(any_bad)
+          : "r"(bad ? 1u : 0u), "n"(kConsumerThreads)
+          : "memory");
+      if (any_bad) {
+        float* out = reinterpret_cast<float*>(smem_raw + (red_base - dyn_base));
+        slow_rows<DT, IK>(p, row0, rows_valid, chunk_begin, chunk_end, out);
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+        if (threadIdx.x < 128) total = out[tj * 32 + trow];
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+      }
 
-    if (threadIdx.x == 0) trace_stamp(p, 10);
-    // ---- per-warp partial results -> red[warp][j][row] fp32 ----
-#pragma unroll
-    for (int a = 1; a < kChains; ++a)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[0][i] += acc[a][i];
-    const uint32_t rbase = red_base + (uint32_t)warp * 512u;
-    if constexpr (M1) {
-      // valid: lanes q_<2: acc[0],acc[1] = rows 4g+2q_, 4g+2q_+1 (k-set 1); lanes q_>=2: acc[2],acc[3] = rows
-      // 4g+2(q_-2), +1 (k-set 2)
-      const int jj = q_ >> 1;
-      const int r = 4 * g_ + 2 * (q_ & 1);
-      sts32(rbase + (uint32_t)(jj * 32 + r) * 4u, __float_as_uint(jj ? acc[0][2] : acc[0][0]));
-      sts32(rbase + (uint32_t)(jj * 32 + r + 1) * 4u, __float_as_uint(jj ? acc[0][3] : acc[0][1]));
-    } else {
-      // acc[0],acc[1] = C[g_][2q_, 2q_+1]: mi = g_/4, rows 4*(2q_)+g_%4 and 4*(2q_+1)+g_%4; acc[2],acc[3]: mi + 2
-      const int mi = g_ >> 2, qq = g_ & 3;
-      sts32(rbase + (uint32_t)(mi * 32 + 8 * q_ + qq) * 4u, __float_as_uint(acc[0][0]));
-      sts32(rbase + (uint32_t)(mi * 32 + 8 * q_ + 4 + qq) * 4u, __float_as_uint(acc[0][1]));
-      sts32(rbase + (uint32_t)((mi + 2) * 32 + 8 * q_ + qq) * 4u, __float_as_uint(acc[0][2]));
-      sts32(rbase + (uint32_t)((mi + 2) * 32 + 8 * q_ + 4 + qq) * 4u, __float_as_uint(acc[0][3]));
-    }
-  }
-  __syncthreads();
-
-  if (threadIdx.x == 0) trace_stamp(p, 11);
-  // ---- CTA-level sums: thread (tj, trow) adds the warps' partials in warp order ----
-  const int nj = M1 ? 1 : p.m;
-  float total = 0.f;
-  const int tj = threadIdx.x >> 5, trow = threadIdx.x & 31;
-  if (threadIdx.x < 128) {
-    if constexpr (M1) {
-      if (tj == 0) {
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-          total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)trow * 4u));
-          total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)(32 + trow) * 4u));
+      if (threadIdx.x < 128) {
+        if (p.splits == 1) {
+          if (tj < nj && trow < rows_valid) p.y[(int64_t)tj * p.y_stride + row0 + trow] = f32_to_dt<DT>(total);
+        } else {
+          exch[tj * 32 + trow] = total;  // one row block per CTA when k is split: exchanged after the loop
         }
       }
-    } else {
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w)
-        total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)(tj * 32 + trow) * 4u));
     }
+    if (threadIdx.x == 0) trace_stamp(p, 11);
   }
 
-  // non-finite sums (Inf/NaN weights) are recomputed row by row so they stay confined to their row
-  const bool bad = threadIdx.x < 128 && tj < nj && trow < rows_valid && !(fabsf(total) <= 3.0e38f);
-  if (__syncthreads_or(bad ? 1 : 0)) {
-    float* out = reinterpret_cast<float*>(smem_raw + (red_base - dyn_base));
-    slow_rows<DT, IK>(p, row0, rows_valid, chunk_begin, chunk_end, out);
-    __syncthreads();
-    if (threadIdx.x < 128) total = out[tj * 32 + trow];
-  }
-
-  if (p.splits == 1) {
-    if (threadIdx.x < 128 && tj < nj && trow < rows_valid)
-      p.y[(int64_t)tj * p.y_stride + row0 + trow] = f32_to_dt<DT>(total);
-    if (threadIdx.x == 0) {
-      trace_stamp(p, 12);
-      if (p.trace != nullptr) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        p.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 15] = smid;
-      }
+  if (p.splits > 1) {
+    // split-k: every CTA of the cluster has published its 32 x nj partials; rank 0 adds them in rank order
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    const int nj = M1 ? 1 : p.m;
+    const int tj = threadIdx.x >> 5, trow = threadIdx.x & 31;
+    const int row0 = (int)blockIdx.x * kRowsPerCta;
+    const int rows_valid = min(kRowsPerCta, p.w_rows - row0);
+    float* part = reinterpret_cast<float*>(smem_raw + kExchOff);
+    if (cluster.block_rank() == 0 && threadIdx.x < 128 && tj < nj) {
+      float sum = 0.f;
+      for (unsigned r = 0; r < (unsigned)p.splits; ++r) sum += cluster.map_shared_rank(part, r)[tj * 32 + trow];
+      if (trow < rows_valid) p.y[(int64_t)tj * p.y_stride + row0 + trow] = f32_to_dt<DT>(sum);
     }
-    return;
+    cluster.sync();  // keep remote shared memory alive until rank 0 has read it
   }
-
-  // split-k: every CTA of the cluster publishes its 32 x nj partials; rank 0 adds them in rank order
-  cg::cluster_group cluster = cg::this_cluster();
-  float* part = reinterpret_cast<float*>(smem_raw + kExchOff);
-  if (threadIdx.x < 128) part[tj * 32 + trow] = total;
-  cluster.sync();
-  if (cluster.block_rank() == 0 && threadIdx.x < 128 && tj < nj) {
-    float sum = total;
-    for (unsigned r = 1; r < (unsigned)p.splits; ++r) {
-      const float* remote = cluster.map_shared_rank(part, r);
-      sum += remote[tj * 32 + trow];
+  if (threadIdx.x == 0) {
+    trace_stamp(p, 12);
+    if (p.trace != nullptr) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 15] = smid;
     }
-    if (trow < rows_valid) p.y[(int64_t)tj * p.y_stride + row0 + trow] = f32_to_dt<DT>(sum);
   }
-  cluster.sync();  // keep remote shared memory alive until rank 0 has read it
 }
 
 unsigned long long* g_trace_buf = nullptr;  // set by tg_debug_set_trace (not part of the public header)
@@ -730,7 +770,15 @@ int launch_one(const Params& p, int row_blocks, cudaStream_t st) {
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)row_blocks, (unsigned)p.splits, 1);
+  // persistent: one CTA (or one k-split cluster) per SM, each walking over its share of the row blocks
+  static thread_local int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
+  const int slots = n_sm / p.splits > 0 ? n_sm / p.splits : 1;
+  cfg.gridDim = dim3((unsigned)(row_blocks < slots ? row_blocks : slots), (unsigned)p.splits, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = kDynSmemBytes;
   cfg.stream = st;
