@@ -19,7 +19,7 @@ _ops_loaded = False
 
 # every symbol include/tinygemm_b200.h declares (checked by tests/test_capi_symbols.py)
 CAPI_SYMBOLS = (
-    "tg_last_error", "tg_version", "tg_launch_count", "tg_reset_launch_count",
+    "tg_set_option", "tg_last_error", "tg_version", "tg_launch_count", "tg_reset_launch_count",
     "tg_convert_to_A", "tg_convert_from_A", "tg_convert_to_B", "tg_convert_from_B",
     "tg_convert_to_Aint4", "tg_convert_to_Aint8", "tg_convert_to_Bint4", "tg_convert_to_Bint8",
     "tg_gemm_w4_rm", "tg_gemm_w8_rm", "tg_gemm_w16_rm",
@@ -48,6 +48,8 @@ def capi():
     lib.tg_version.restype = ctypes.c_char_p
     lib.tg_launch_count.restype = ctypes.c_uint64
     lib.tg_reset_launch_count.restype = None
+    lib.tg_set_option.argtypes = [i32, i32]
+    lib.tg_set_option.restype = i32
     lib.tg_convert_to_A.argtypes = [vp, vp, i64, i64, vp]
     lib.tg_convert_from_A.argtypes = [vp, vp, i64, i64, vp]
     lib.tg_convert_to_B.argtypes = [vp, vp, i64, i64, i32, vp]

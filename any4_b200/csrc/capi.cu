@@ -18,6 +18,7 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += (uint64_t)n; }
 
+void set_w4_options(int pdl, int static_weights);
 int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
                         const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
                         tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st);
@@ -103,6 +104,15 @@ const char* tg_last_error(void) { return g_err; }
 const char* tg_version(void) { return "tinygemm_b200 0.1 sm_100a"; }
 uint64_t tg_launch_count(void) { return g_launches; }
 void tg_reset_launch_count(void) { g_launches = 0; }
+
+int tg_set_option(tg_option option, int value) {
+  switch (option) {
+    case TG_OPT_PDL: set_w4_options(value != 0, -1); return TG_OK;
+    case TG_OPT_STATIC_WEIGHTS: set_w4_options(-1, value != 0); return TG_OK;
+  }
+  set_error("tg_set_option: unknown option %d", (int)option);
+  return TG_ERR_INVALID_ARGUMENT;
+}
 
 int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
                   const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,

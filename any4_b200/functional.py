@@ -24,6 +24,16 @@ _VALID_W_INNER_K = {
 }
 
 
+def set_static_weights(flag=True):
+    """B200 extension (not in the reference): promise that packed weights / LUTs / scales are not produced by the
+    kernel launched right before a GEMV on the same stream, so the weight stream of each GEMV may start while the
+    previous kernel is still finishing (include/tinygemm_b200.h: TG_OPT_STATIC_WEIGHTS).  True for a model whose
+    layers were packed once with `reshape_weight()`; keep it off when calling the `reshape_weight=True` wrappers."""
+    rc = _native.capi().tg_set_option(1, 1 if flag else 0)
+    if rc != 0:
+        raise RuntimeError(_native.last_error())
+
+
 def valid_tinygemm_kernel_call(functional_api, w_inner_k):
     """True when (api, w_inner_k) is a supported any4 combination, else None (as the reference)."""
     if w_inner_k in _VALID_W_INNER_K.get(functional_api, ()):

@@ -49,6 +49,20 @@ typedef enum {
   TG_WEIGHT_A = 0  /* weightOnRight = false: y = (W x^T)^T, W in "A" layout (16-row tiles) */
 } tg_weight_side;
 
+/* process-wide tuning options (no counterpart in the reference; defaults reproduce its semantics exactly) */
+typedef enum {
+  /* launch the GEMV kernels with programmatic stream serialization so that a kernel's prologue overlaps the
+   * tail of the previous kernel in the stream (default 1).  Ordering is preserved: the kernel waits for the
+   * previous one before it reads activations / writes its output. */
+  TG_OPT_PDL = 0,
+  /* promise that packed weights, LUTs, scales/zeros and exponents passed to the GEMV entry points are never
+   * produced by the kernel launched just before them on the same stream (true for a loaded model; NOT true for
+   * convert-then-GEMM sequences such as functional.linear_*(reshape_weight=True)).  With the promise (and PDL)
+   * the weight stream starts before the previous kernel has finished.  Default 0. */
+  TG_OPT_STATIC_WEIGHTS = 1
+} tg_option;
+int tg_set_option(tg_option option, int value);
+
 const char* tg_last_error(void);
 /* library / build identification, e.g. "tinygemm_b200 0.1 sm_100a" */
 const char* tg_version(void);

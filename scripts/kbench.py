@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Quick graph-timed us/GEMV of the hot kernel for a few shapes (tuning helper; env knobs TG_W4_*)."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import tinygemm  # noqa: E402,F401
+from bench import G, algorithmic_bytes, synth_layer  # noqa: E402
+
+
+def main():
+    from any4_b200 import functional as tgf
+    tgf.set_static_weights(os.environ.get('KB_STATIC', '1') == '1')
+    _native_lib = __import__('any4_b200._native', fromlist=['capi']).capi()
+    _native_lib.tg_set_option(0, int(os.environ.get('KB_PDL', '1')))
+    dev = torch.device("cuda:0")
+    op = torch.ops.tinygemm.tinygemm_y_f16RM_x_f16RM_w_any4TC
+    out = {}
+    for n in [int(a) for a in sys.argv[1:]] or [4096, 8192, 11008]:
+        k = n
+        nbytes = algorithmic_bytes(n, k)
+        copies = max(3, int(float(os.environ.get('KB_L2X', '2.6')) * 126e6 / nbytes) + 1)
+        layers = [synth_layer(n, k, 10 + i, dev) for i in range(copies)]
+        x = torch.randn(1, k, device=dev).bfloat16()
+
+        def step():
+            for w, lut, sz in layers:
+                op(x, w, G, sz, lut, True)
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (10 * copies)
+        out[n] = round(us, 2)
+        del layers
+        torch.cuda.empty_cache()
+    print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("TG_W4")}, "l2x": os.environ.get("KB_L2X", "2.6"), "us_per_gemv": out,
+                      "GBps": {n: round(algorithmic_bytes(n, n) / us / 1e3) for n, us in out.items()}}))
+
+
+if __name__ == "__main__":
+    main()
