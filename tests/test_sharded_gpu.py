@@ -1,0 +1,68 @@
+"""GPU (>= 2 devices): the row-sharded path over NCCL - every rank runs the CUDA GEMV on its row shard, ONE
+all-reduce on the zero-padded m x n output, result bit-identical to the single-GPU output."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from any4_b200.modules import Any4Linear, RowShardedLinear
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ok = True
+    for (n, k, m, per_row) in [(4096, 4096, 1, True), (1024, 2048, 4, True), (512, 1024, 3, False)]:
+        gen = torch.Generator().manual_seed(100 + n + m)
+        full = Any4Linear(k, n, bias=True, device=dev, dtype=torch.bfloat16, group_size=128, per_row=per_row)
+        full.weight.data = torch.randint(0, 16, (n, k), generator=gen, dtype=torch.int32).to(dev)
+        lut = ((torch.rand(n if per_row else 1, 16, generator=gen) * 15).sort(1).values.bfloat16() - 8)
+        full.lut.data = (lut if per_row else lut[0]).contiguous().to(dev)
+        sz = torch.stack([torch.rand(k // 128, n, generator=gen) * 0.01 + 0.001, torch.randn(k // 128, n, generator=gen) * 0.01], 2)
+        full.scales_and_zeros.data = sz.bfloat16().to(dev)
+        full.bias.data = torch.randn(n, generator=gen).bfloat16().to(dev)
+        full.reshape_weight(4)
+        x = torch.randn(m, k, generator=gen).bfloat16().to(dev)
+        want = full(x)
+        got = RowShardedLinear(full, rank, world)(x)
+        ok = ok and torch.equal(got, want)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        q.put(bool(flag.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_row_sharded_nccl(world):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok
