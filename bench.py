@@ -254,7 +254,7 @@ def run_ours(args):
         lib.tg_reset_launch_count()
         step()
         launches = int(lib.tg_launch_count()) * steps  # our kernels per step (same under graph replay) x K
-        ms = time_gemv_set(step, copies, steps, warmup, dist, graph=(world == 1 and not args.no_graph))
+        ms = time_gemv_set(step, copies, steps, warmup, dist, graph=not args.no_graph)
         out = {"n": n, "k": k, "copies": copies, "ms": ms, "launches": launches,
                "us_per_gemv": ms * 1e3 / (steps * copies),
                "gbps": nbytes * copies * steps / (ms * 1e-3) / 1e9}
@@ -302,7 +302,7 @@ def run_ours(args):
             "config": {
                 "workload": "any4-bf16 GEMV m=1 n=k=4096 g=128 per-row LUT (BASELINE configs[1])",
                 "gemvs_per_step": head["copies"],
-                "launch": "eager" if (args.no_graph or world > 1) else "one CUDA graph per step (replayed K times)",
+                "launch": "eager" if args.no_graph else "one CUDA graph per step (replayed K times)",
                 "l2_policy": f"inputs larger than L2: {head['copies']} distinct weight sets = "
                              f"{head['copies'] * nbytes / 1e6:.0f} MB rotated every step",
                 "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world} + NCCL all-reduce on y",
