@@ -281,10 +281,59 @@ def run_ours(args):
         r = bench_shape(args.profile_shape, args.profile_shape, args.steps, args.warmup, False)
         print(json.dumps(r))
         return
+    def format_sweep():
+        """BASELINE configs[3]: int4 / nf4 (any4, one global LUT) / any4 row-wise / mx4 x m in {1,4,8,16} at 4096^2,
+        plus the A-layout int4 path (Int4Linear default), int8 and 16-bit weights at m = 1.  us per GEMM from a CUDA
+        graph over `copies` distinct weight sets; informational (not part of the headline value)."""
+        ops = torch.ops.tinygemm
+        n = k = HEADLINE
+        copies = max(3, int(2.6 * 126e6 / algorithmic_bytes(n, k)) + 1)
+        gen = torch.Generator(device=dev).manual_seed(99)
+        ws = [synth_layer(n, k, 500 + i, dev) for i in range(copies)]
+        nf4 = torch.tensor([-1.0, -0.6962, -0.5251, -0.3949, -0.2844, -0.1848, -0.0911, 0.0, 0.0796, 0.1609, 0.2461,
+                            0.3379, 0.4407, 0.5626, 0.723, 1.0], device=dev).bfloat16()
+        sz32 = torch.stack([torch.rand(k // 32, n, generator=gen, device=dev) * 0.01 + 0.001,
+                            torch.randn(k // 32, n, generator=gen, device=dev) * 0.01], 2).bfloat16().contiguous()
+        exps = torch.randint(118, 130, (n, k // 32), generator=gen, device=dev, dtype=torch.int32).to(torch.uint8)
+
+        def timed(fn):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return round(e0.elapsed_time(e1) * 1e3 / (5 * copies), 2)
+
+        out = {}
+        for m in (1, 4, 8, 16):
+            x = torch.randn(m, k, device=dev).bfloat16()
+            out[f"m{m}"] = {
+                "any4_rowwise_g128": timed(lambda: [ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(x, w, G, sz, lut, True) for w, lut, sz in ws]),
+                "nf4_global_g128": timed(lambda: [ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(x, w, G, sz, nf4, True) for w, lut, sz in ws]),
+                "int4_g128": timed(lambda: [ops.tinygemm_y_f16RM_x_f16RM_w_int4TC(x, w, G, sz, True) for w, lut, sz in ws]),
+                "mx4_g32": timed(lambda: [ops.tinygemm_y_f16RM_x_f16RM_w_mx4TC(x, w, 32, exps, True) for w, lut, sz in ws]),
+            }
+        x = torch.randn(1, k, device=dev).bfloat16()
+        wa = [w.view(n // 16, k // 64, 32, 4) for w, _, _ in ws]       # same bytes viewed as the A int4 layout (ik = 4)
+        out["m1"]["int4_g128_A_layout(Int4Linear default)"] = timed(
+            lambda: [ops.tinygemm_y_f16RM_x_f16RM_w_int4TC(w, x, G, sz, False) for w, (_, _, sz) in zip(wa, ws)])
+        out["unit"] = "us per GEMM at n=k=4096, bf16, CUDA graph, weights rotated through > 2.5x L2"
+        return out
+
     sampler = ClockSampler(local) if rank == 0 else None
     head = bench_shape(HEADLINE, HEADLINE, args.steps, args.warmup, True)
     extra = [bench_shape(s, s, max(3, args.steps // 2), args.warmup, False) for s in EXTRA_SHAPES]
     clocks = sampler.stop() if sampler else None
+    sweep = format_sweep() if (rank == 0 and world == 1 and not args.no_sweep) else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -320,6 +369,8 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if sweep is not None:
+            line["config"]["format_sweep_us"] = sweep
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -333,6 +384,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the informational format / m sweep")
     ap.add_argument("--profile-shape", type=int, default=0, help="(for ncu) run only the n=k=N GEMV set")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

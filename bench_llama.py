@@ -1,0 +1,182 @@
+#!/usr/bin/env python
+"""bench_llama.py - BASELINE.json configs[2] / configs[4]: Llama-3-8B any4 (g = 128, per-row LUT) single-token
+decode, batch 1, synthetic weights / prompt, on 1 GPU or row-sharded over N GPUs (one NCCL all-reduce per Linear).
+
+  python bench_llama.py [--steps K] [--warmup W] [--ctx L] [--layers 32]
+  python -m torch.distributed.run --nproc-per-node N ... bench_llama.py --gpus N
+
+The model is a bench harness around the hot path, not a product component: every nn.Linear of the decoder
+stack (q, k, v, o, gate, up, down; `lm_head` stays bf16 as in the reference, quantize.py:34-36) is an
+`any4_b200.modules.Any4Linear` filled with synthetic packed codes / LUTs / scales (the k-means quantizer is
+out of scope and irrelevant for timing); attention (static KV cache of `--ctx` synthetic tokens, torch SDPA),
+RMSNorm, RoPE and SiLU are stock torch ops.  One decode step is captured in a CUDA graph and replayed.
+Architecture: public Llama-3-8B card (hidden 4096, 32 layers, 32 heads, 8 KV heads, intermediate 14336,
+vocab 128256, rope theta 500000, rms eps 1e-5).
+Reports tok/s = 1 / step latency and the fraction of the HBM roofline for the bytes a step must stream.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+from bench import ClockSampler, G, measured_peak, synth_layer  # noqa: E402
+
+HID, LAYERS, HEADS, KV_HEADS, INTER, VOCAB, HEAD_DIM = 4096, 32, 32, 8, 14336, 128256, 128
+THETA, EPS = 500000.0, 1e-5
+
+
+def any4_bytes(n, k):
+    return n * k // 2 + (k // G) * n * 4 + n * 32
+
+
+def make_linear(n, k, seed, dev, rank, world):
+    from any4_b200.modules import Any4Linear, RowShardedLinear
+
+    lin = Any4Linear(k, n, bias=False, device=dev, dtype=torch.bfloat16, group_size=G)
+    w, lut, sz = synth_layer(n, k, seed, dev)
+    # keep activations tame through 32 random layers: centre the per-group zero, small scales
+    lin.weight.data, lin.lut.data, lin.scales_and_zeros.data = w, lut, sz * 0.25
+    lin.weight_reshaped = True
+    return RowShardedLinear(lin, rank, world) if world > 1 else lin
+
+
+class Block(torch.nn.Module):
+    def __init__(self, idx, dev, rank, world, ctx):
+        super().__init__()
+        s = 1000 * idx
+        self.q = make_linear(HID, HID, s + 1, dev, rank, world)
+        self.k = make_linear(KV_HEADS * HEAD_DIM, HID, s + 2, dev, rank, world)
+        self.v = make_linear(KV_HEADS * HEAD_DIM, HID, s + 3, dev, rank, world)
+        self.o = make_linear(HID, HID, s + 4, dev, rank, world)
+        self.gate = make_linear(INTER, HID, s + 5, dev, rank, world)
+        self.up = make_linear(INTER, HID, s + 6, dev, rank, world)
+        self.down = make_linear(HID, INTER, s + 7, dev, rank, world)
+        self.n1 = torch.ones(HID, device=dev, dtype=torch.bfloat16)
+        self.n2 = torch.ones(HID, device=dev, dtype=torch.bfloat16)
+        gen = torch.Generator(device=dev).manual_seed(s + 9)
+        self.kc = torch.randn(1, KV_HEADS, ctx + 1, HEAD_DIM, device=dev, generator=gen).bfloat16()
+        self.vc = torch.randn(1, KV_HEADS, ctx + 1, HEAD_DIM, device=dev, generator=gen).bfloat16()
+        self.ctx = ctx
+
+    def forward(self, h, cos, sin):
+        x = F.rms_norm(h, (HID,), self.n1, EPS)
+        q = self.q(x).view(1, HEADS, 1, HEAD_DIM)
+        k = self.k(x).view(1, KV_HEADS, 1, HEAD_DIM)
+        v = self.v(x).view(1, KV_HEADS, 1, HEAD_DIM)
+
+        def rope(t):
+            t1, t2 = t[..., : HEAD_DIM // 2], t[..., HEAD_DIM // 2:]
+            return t * cos + torch.cat((-t2, t1), -1) * sin
+
+        q, k = rope(q), rope(k)
+        self.kc[:, :, self.ctx:] = k
+        self.vc[:, :, self.ctx:] = v
+        a = F.scaled_dot_product_attention(q, self.kc, self.vc, enable_gqa=True)
+        h = h + self.o(a.reshape(1, HID))
+        x = F.rms_norm(h, (HID,), self.n2, EPS)
+        return h + self.down(F.silu(self.gate(x)) * self.up(x))
+
+
+class Llama(torch.nn.Module):
+    def __init__(self, dev, rank, world, ctx, layers):
+        super().__init__()
+        gen = torch.Generator(device=dev).manual_seed(7)
+        self.emb = (torch.randn(VOCAB, HID, device=dev, generator=gen) * 0.02).bfloat16()
+        self.blocks = torch.nn.ModuleList([Block(i, dev, rank, world, ctx) for i in range(layers)])
+        self.norm = torch.ones(HID, device=dev, dtype=torch.bfloat16)
+        self.lm_head = (torch.randn(VOCAB, HID, device=dev, generator=gen) * 0.02).bfloat16()
+        pos = torch.tensor([float(ctx)], device=dev)
+        inv = 1.0 / (THETA ** (torch.arange(0, HEAD_DIM, 2, device=dev).float() / HEAD_DIM))
+        ang = torch.cat([pos[:, None] * inv[None], pos[:, None] * inv[None]], -1)
+        self.cos, self.sin = ang.cos().bfloat16().view(1, 1, 1, HEAD_DIM), ang.sin().bfloat16().view(1, 1, 1, HEAD_DIM)
+
+    def forward(self, tok):
+        h = self.emb[tok].view(1, HID)
+        for b in self.blocks:
+            h = b(h, self.cos, self.sin)
+        return F.linear(F.rms_norm(h, (HID,), self.norm, EPS), self.lm_head)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--ctx", type=int, default=128)
+    ap.add_argument("--layers", type=int, default=LAYERS)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+    from any4_b200 import _native
+    from any4_b200 import functional as tgf
+
+    tgf.set_static_weights(True)
+    lib = _native.capi()
+    with torch.no_grad():
+        model = Llama(dev, rank, world, args.ctx, args.layers)
+        tok = torch.tensor([1], device=dev)
+        lib.tg_reset_launch_count()
+        logits = model(tok)
+        launches = int(lib.tg_launch_count())
+        assert torch.isfinite(logits.float()).all(), "synthetic model produced non-finite logits"
+        for _ in range(args.warmup):
+            model(tok)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = model(tok)
+        g.replay()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        per_layer = 2 * any4_bytes(HID, HID) + 2 * any4_bytes(KV_HEADS * HEAD_DIM, HID) + 2 * any4_bytes(INTER, HID) + any4_bytes(HID, INTER)
+        quant_bytes = per_layer * args.layers
+        head_bytes = VOCAB * HID * 2
+        kv_bytes = args.layers * 2 * KV_HEADS * (args.ctx + 1) * HEAD_DIM * 2
+        total = quant_bytes / world + head_bytes + kv_bytes  # per GPU: its shard of the any4 layers, replicated head/KV
+        peak, src = measured_peak()
+        print(json.dumps({
+            "metric": "llama3_8b_any4_g128_decode_tok_per_s", "value": 1e3 / ms, "unit": "tok/s", "n_gpus": world,
+            "ms_per_token": ms, "steps": args.steps, "warmup": args.warmup, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "Llama-3-8B any4 g=128 single-token decode, batch 1 (BASELINE configs[2]/[4])",
+                       "layers": args.layers, "kv_context": args.ctx, "launch": "one CUDA graph per token",
+                       "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world}, NCCL all-reduce per Linear",
+                       "lm_head": "bf16 (not quantized, as in the reference)"},
+            "bytes_per_token_per_gpu": total,
+            "roofline": {"bound": "hbm", "achieved": total / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": total / (ms * 1e-3) / 1e9 / peak, "peak_source": src + " (of measured)"},
+            "gemv_launches_per_token": launches, "clocks": clocks}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
