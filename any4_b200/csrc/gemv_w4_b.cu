@@ -45,14 +45,12 @@ namespace {
 constexpr int kWarps = 16;             // consumer warps (4 per SM sub-partition); warp 16 is the TMA producer
 constexpr int kThreads = (kWarps + 1) * 32;
 constexpr int kConsumerThreads = kWarps * 32;
-constexpr int kGroupWarps = 8;         // consumer warps that share one stage; the two groups take alternate stages
-constexpr int kStages = 6;             // CTA-wide ring depth (96 KB of weights in flight per SM)
+constexpr int kStages = 3;             // CTA-wide ring depth (96 KB of weights in flight per SM)
 constexpr int kRowsPerCta = 32;        // = 4 n-tiles
 constexpr int kChunkK = 128;           // k elements one warp consumes per stage
-constexpr int kStageK = kGroupWarps * kChunkK;     // 1024 k per stage: small enough that the first data is consumed
-                                                   // ~0.4 us after the stream starts (one SM requests ~40 GB/s)
-constexpr int kTileStageBytes = kStageK * 4;       // one n-tile (8 rows) x 1024 k = 4 KiB = one bulk copy
-constexpr int kStageBytes = 4 * kTileStageBytes;   // 16 KiB
+constexpr int kStageK = kWarps * kChunkK;          // 2048 k per stage
+constexpr int kTileStageBytes = kStageK * 4;       // one n-tile (8 rows) x 2048 k = 8 KiB = one bulk copy
+constexpr int kStageBytes = 4 * kTileStageBytes;   // 32 KiB
 constexpr int kTileChunkBytes = 512;   // bytes of one n-tile per 128 k
 // Shared-memory carve-up, all relative to the start W0 of the CTA's dynamic window (which is NOT
 // 0-based for CTAs of a cluster):
@@ -363,13 +361,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   const int row_blocks = (p.w_rows + kRowsPerCta - 1) / kRowsPerCta;
   const int n_blk = (row_blocks - (int)blockIdx.x + G - 1) / G;   // row blocks of this CTA (>= 1)
 
-  // k range of this CTA in 128-wide chunks; a stage is kGroupWarps consecutive chunks, consumed by warp group
-  // (stage index & 1): one chunk per warp of that group
+  // k range of this CTA in 128-wide chunks; a stage is kWarps consecutive chunks (one per consumer warp)
   const int chunks_total = (p.k + kChunkK - 1) / kChunkK;
   const int chunks_per_split = (chunks_total + p.splits - 1) / p.splits;
   const int chunk_begin = split * chunks_per_split;
   const int chunk_end = min(chunks_total, chunk_begin + chunks_per_split);
-  const int n_stage_iters = (max(chunk_end - chunk_begin, 0) + kGroupWarps - 1) / kGroupWarps;
+  const int n_stage_iters = (max(chunk_end - chunk_begin, 0) + kWarps - 1) / kWarps;
   const int n_groups = p.k >> p.glog2;
 
   // ---- shared memory carve-up (window addresses, see the constants above) ----
@@ -400,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       const int s = jj % kStages;
       const int tiles_valid = min(kRowsPerCta, p.w_rows - rb * kRowsPerCta) >> 3;
       const uint8_t* wsrc = p.w + (int64_t)(rb * 4) * p.tile_stride;
-      const int c0 = chunk_begin + j * kGroupWarps;
+      const int c0 = chunk_begin + j * kWarps;
       const int k0 = c0 * kChunkK;
       const int kvalid = min(min(kStageK, (chunk_end - c0) * kChunkK), p.k - k0);
       const uint32_t bytes = (uint32_t)kvalid * 4u;  // per n-tile: 8 rows * kvalid / 2
@@ -417,14 +414,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
         mbar_init(full_bar + s * 8, 1);
-        mbar_init(empty_bar + s * 8, kGroupWarps);
+        mbar_init(empty_bar + s * 8, kWarps);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       pol = l2_evict_first_policy();
       trace_stamp(p, 2);
       if (n_stage_iters > 0) issue_stage((int)blockIdx.x, 0, 0);
-      trace_stamp(p, 1);
     }
     __syncwarp();
     // tell the consumers the barriers exist (they wait on named barrier 2 before their main loop)
@@ -570,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     const bool has_row23 = M1 ? false : (set1 ? p.m > 2 : p.m > 3);
     const uint32_t xa01 = (x_active && has_row01) ? 1u : 0u;
     const uint32_t xa23 = (x_active && has_row23) ? 1u : 0u;
-    const uint32_t w_lane_off = (uint32_t)(lane >> 3) * kTileStageBytes + (uint32_t)(warp % kGroupWarps) * kTileChunkBytes +
+    const uint32_t w_lane_off = (uint32_t)(lane >> 3) * kTileStageBytes + (uint32_t)warp * kTileChunkBytes +
                                 (uint32_t)(lane & 7) * Geo<IK>::kRowStride;
     uint32_t xr0[4] = {0u, 0u, 0u, 0u}, xr1[4] = {0u, 0u, 0u, 0u};  // x fragments (stay zero on inactive lanes)
     uint32_t xs0[4] = {0u, 0u, 0u, 0u}, xs1[4] = {0u, 0u, 0u, 0u};  // rows mi+2 (!M1)
@@ -579,8 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     const int tj = threadIdx.x >> 5, trow = threadIdx.x & 31;
     float* const exch = reinterpret_cast<float*>(smem_raw + kExchOff);
 
-    const int group = warp / kGroupWarps;  // consumer group 0 / 1
-    const int wig = warp % kGroupWarps;    // warp in group = chunk within a stage
+    int jj = 0;  // stage counter across row blocks (ring position / parity)
     for (int b = 0; b < n_blk; ++b) {
       const int rb = (int)blockIdx.x + b * G;
       const int row0 = rb * kRowsPerCta;
@@ -591,18 +586,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[a][i] = 0.f;
 
-      // global stage index (ring position / parity) of stage j of this block: jj = b * n_stage_iters + j; the
-      // group alternation follows jj so that it continues seamlessly across row blocks
-      const int jj0 = b * n_stage_iters;
-      bool preloaded = false;
-      for (int j = (group + jj0) & 1; j < n_stage_iters; j += 2) {
-        const int jj = jj0 + j;
+      for (int j = 0; j < n_stage_iters; ++j, ++jj) {
         const int s = jj % kStages;
-        const int c = chunk_begin + j * kGroupWarps + wig;  // this warp's chunk in stage j
-        if (j + 2 >= n_stage_iters && b + 1 < n_blk) {  // this group's last stage of the block:
-          load_block_regs(rb + G);                      // fetch the next block's LUT / group words
-          preloaded = true;
-        }
+        const int c = chunk_begin + j * kWarps + warp;  // this warp's chunk in stage j
+        if (j == n_stage_iters - 1 && b + 1 < n_blk) load_block_regs(rb + G);  // next block's LUT / group words
 
         // group (scale, zero) of the four tile pairs (32 k each) of this chunk, from the staged words
         uint32_t s2[4], z2[4];
@@ -632,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
         __syncwarp();
         while (!mbar_try(full_bar + s * 8, (uint32_t)(jj / kStages) & 1u)) {
         }
-        if (threadIdx.x == 0 && jj < 8 && !(jj & 1)) trace_stamp(p, 6 + (jj >> 1));
+        if (threadIdx.x == 0 && jj < 4) trace_stamp(p, 6 + jj);
         // A chunk is always processed whole: beyond k the staged activations are zero, so whatever bytes the
         // stage holds there contribute 0 (finite weights; the non-finite case is handled after the loop).
         if (c < chunk_end && !(p.flags & 2)) {
@@ -695,7 +682,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar + s * 8) : "memory");
       }
-      if (!preloaded && b + 1 < n_blk) load_block_regs(rb + G);  // (a group without a stage in this block)
       if (threadIdx.x == 0 && b == 0) trace_stamp(p, 10);
 
       // ---- per-warp partial results -> red[warp][j][row] fp32 ----
@@ -906,7 +892,7 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
   // k is split across a thread-block cluster (a) when the row blocks alone cannot fill the machine and
   // (b) as far as needed for one CTA's activations and group words to fit its shared-memory staging areas
   int splits = 1;
-  while (splits < 8 && row_blocks * splits * 2 <= 148 && chunks / (splits * 2) >= kWarps) splits *= 2;  // >= 2 stages each
+  while (splits < 8 && row_blocks * splits * 2 <= 148 && chunks / (splits * 2) >= kWarps) splits *= 2;
   auto fits = [&](int sp) {
     const int64_t cps = div_up(chunks, sp);                         // chunks per split
     const int64_t groups = cps * kChunkK / group + 2;               // groups touched by one split (upper bound)

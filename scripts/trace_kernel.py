@@ -14,7 +14,7 @@ from any4_b200 import _native  # noqa: E402
 import tinygemm  # noqa: E402,F401
 from bench import synth_layer, G  # noqa: E402
 
-NAMES = ["entry", "stage0_issued", "tma_start", "tma_refill0", "staged", "cons_sync", "full0", "full1", "full2", "full3",
+NAMES = ["entry", "loads_issued", "tma_start", "tma_refill0", "staged", "cons_sync", "full0", "full1", "full2", "full3",
          "loop_end", "cta_sync", "exit"]
 
 
