@@ -89,6 +89,8 @@ struct Params {
   int64_t y_stride;      // elements between activation rows of y (= total w_rows)
   int x_row_bytes;       // staged bytes per activation row, multiple of 256 (whole 128-k chunks)
   int splits;            // cluster size along k (gridDim.y)
+  int chunks_per_split;  // ceil(ceil(k / 128) / splits)       } precomputed on the host: no integer
+  int blk_q, blk_r;      // row_blocks / gridDim.x and % gridDim.x  } divisions on the kernel's critical start-up path
   int flags;             // bit 0: request the first stage alone (staged pipeline fill); bit 1 (debug): skip the
                          // dequant/mma body (pure streaming); bit 3: weights/LUT/scales are static (PDL early start)
   unsigned long long* trace;  // optional [CTAs][16] globaltimer stamps (debug, tg_debug_set_trace)
@@ -358,15 +360,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
   if (!static_w) asm volatile("griddepcontrol.wait;" ::: "memory");
   const int split = blockIdx.y;                 // k split (rank in cluster)
   const int G = (int)gridDim.x;
-  const int row_blocks = (p.w_rows + kRowsPerCta - 1) / kRowsPerCta;
-  const int n_blk = (row_blocks - (int)blockIdx.x + G - 1) / G;   // row blocks of this CTA (>= 1)
+  const int n_blk = p.blk_q + ((int)blockIdx.x < p.blk_r ? 1 : 0);   // row blocks of this CTA (>= 1)
 
   // k range of this CTA in 128-wide chunks; a stage is kWarps consecutive chunks (one per consumer warp)
-  const int chunks_total = (p.k + kChunkK - 1) / kChunkK;
-  const int chunks_per_split = (chunks_total + p.splits - 1) / p.splits;
-  const int chunk_begin = split * chunks_per_split;
-  const int chunk_end = min(chunks_total, chunk_begin + chunks_per_split);
-  const int n_stage_iters = (max(chunk_end - chunk_begin, 0) + kWarps - 1) / kWarps;
+  const int chunks_total = (p.k + kChunkK - 1) >> 7;
+  const int chunk_begin = split * p.chunks_per_split;
+  const int chunk_end = min(chunks_total, chunk_begin + p.chunks_per_split);
+  const int n_stage_iters = (max(chunk_end - chunk_begin, 0) + kWarps - 1) >> 4;
+  static_assert(kChunkK == 128 && kWarps == 16, "shifts above");
   const int n_groups = p.k >> p.glog2;
 
   // ---- shared memory carve-up (window addresses, see the constants above) ----
@@ -807,7 +808,11 @@ int launch_one(const Params& p, int row_blocks, cudaStream_t st) {
   }
   static const bool persist = getenv("TG_W4_PERSIST") == nullptr || atoi(getenv("TG_W4_PERSIST")) != 0;  // tuning knob
   const int slots = !persist ? row_blocks : (n_sm / p.splits > 0 ? n_sm / p.splits : 1);
-  cfg.gridDim = dim3((unsigned)(row_blocks < slots ? row_blocks : slots), (unsigned)p.splits, 1);
+  const int gx = row_blocks < slots ? row_blocks : slots;
+  Params pp = p;
+  pp.blk_q = row_blocks / gx;
+  pp.blk_r = row_blocks % gx;
+  cfg.gridDim = dim3((unsigned)gx, (unsigned)p.splits, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = kDynSmemBytes;
   cfg.stream = st;
@@ -827,7 +832,7 @@ int launch_one(const Params& p, int row_blocks, cudaStream_t st) {
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, pp);
   if (e != cudaSuccess) {
     set_error("gemv_w4_b launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -908,7 +913,8 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
   p.trace = g_trace_buf;
   static const int env_flags = getenv("TG_W4_FLAGS") ? atoi(getenv("TG_W4_FLAGS")) : 0;  // tuning knob
   p.flags = env_flags | (g_static_weights ? 8 : 0);
-  p.x_row_bytes = (int)(div_up(chunks, splits) * 256);  // one split's activations, whole 128-k chunks
+  p.chunks_per_split = (int)div_up(chunks, splits);
+  p.x_row_bytes = p.chunks_per_split * 256;  // one split's activations, whole 128-k chunks
 
   if (dt == TG_BF16)
     return launch_ik<TG_BF16>(p, ik, row_blocks, rows_x, (const uint16_t*)x, (uint16_t*)y, st);
