@@ -229,9 +229,7 @@ int launch(const GParams& p, cudaStream_t st) {
 
 template <Kind KIND>
 int dispatch(const GParams& p, tg_weight_side side, tg_dtype dt, cudaStream_t st) {
-  if constexpr (KIND == W4) {
-    return dt == TG_BF16 ? launch<TG_BF16, W4, true>(p, st) : launch<TG_FP16, W4, true>(p, st);
-  } else {
+  {
     if (side == TG_WEIGHT_A) return dt == TG_BF16 ? launch<TG_BF16, KIND, true>(p, st) : launch<TG_FP16, KIND, true>(p, st);
     return dt == TG_BF16 ? launch<TG_BF16, KIND, false>(p, st) : launch<TG_FP16, KIND, false>(p, st);
   }
@@ -240,34 +238,6 @@ int dispatch(const GParams& p, tg_weight_side side, tg_dtype dt, cudaStream_t st
 int glog2_of(int group) { return group == 32 ? 5 : group == 64 ? 6 : group == 128 ? 7 : 8; }
 
 }  // namespace
-
-// A-layout int4 / any4 / mx4
-int launch_gemm_w4_rm_A(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
-                        const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
-                        tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st) {
-  GParams p{};
-  p.w = reinterpret_cast<const uint32_t*>(w);
-  p.x = (const uint16_t*)x;
-  p.y = (uint16_t*)y;
-  p.sz = (const uint16_t*)sz;
-  p.exps = exps;
-  p.is_mx4 = fmt == TG_W4_MX4;
-  if (fmt == TG_W4_ANY4_GLOBAL || fmt == TG_W4_ANY4_ROWWISE) {
-    p.lut = (const uint16_t*)lut;
-    p.lut_stride = fmt == TG_W4_ANY4_ROWWISE ? 16 : 0;
-  } else {
-    p.lut = const_lut;
-    p.lut_stride = 0;
-  }
-  p.rows_x = (int)rows_x;
-  p.w_rows = (int)w_rows;
-  p.k = (int)k;
-  p.k_tiles = (int)div_up(k, 16);
-  p.ik = ik;
-  p.outer_k = (int)div_up(p.k_tiles, ik);
-  p.glog2 = glog2_of(group);
-  return dispatch<W4>(p, TG_WEIGHT_A, dt, st);
-}
 
 int launch_gemm_w8_rm(void* y, const void* x, const int32_t* w, const void* sz, int64_t rows_x, int64_t w_rows,
                       int64_t k, int group, int ik, tg_weight_side side, tg_dtype dt, cudaStream_t st) {
