@@ -62,7 +62,7 @@ struct GeoA<1> {  // chunk = [8 super-tiles][32 lanes][1 word]; a unit = the fou
 
 // exact per-row fallback for non-finite sums (see gemv_w4_b.cu: slow_rows); out[row 0..31] fp32
 template <tg_dtype DT, int IK>
-__device__ __noinline__ void slow_rows_a(const Params& p, int row0, int rows_valid, int chunk_begin, int chunk_end,
+__device__ __noinline__ void slow_rows_a(const Params p, int row0, int rows_valid, int chunk_begin, int chunk_end,
                                          float* out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp >= kWarps) return;

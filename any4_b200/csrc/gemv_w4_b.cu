@@ -89,7 +89,7 @@ struct Geo<8> {  // slice = [1 super-tile][32 lanes][4 words]; row g at +g*64
 // (tests/tinygemm/test_tinygemm_mx4.py:443-506).  out[mi][row] fp32.
 // ---------------------------------------------------------------------------------------
 template <tg_dtype DT, int IK>
-__device__ __noinline__ void slow_rows(const Params& p, int row0, int rows_valid, int chunk_begin, int chunk_end,
+__device__ __noinline__ void slow_rows(const Params p, int row0, int rows_valid, int chunk_begin, int chunk_end,
                                        float* out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp >= kWarps) return;
@@ -320,30 +320,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       // activations, permuted so that (x[16t+i], x[16t+i+8]) are adjacent:
       //   xp[16t + 2i] = x[16t + i], xp[16t + 2i + 1] = x[16t + i + 8], i = 0..7
       // linear byte offset o of row r lives at x_base + ((r*x_row_bytes + o) / 128) * 256 + (o % 128)
-      uint32_t px1[kPre], px2[kPre];
-      const uint32_t* xr0p = reinterpret_cast<const uint32_t*>(p.x);
-#pragma unroll
-      for (int i = 0; i < kPre; ++i) {
-        const int it = item_begin + (int)threadIdx.x + i * kConsumerThreads;
-        px1[i] = px2[i] = 0u;
-        if (it < min(item_end, item_valid_end)) {
-          px1[i] = xr0p[(it >> 2) * 8 + (it & 3)];
-          px2[i] = xr0p[(it >> 2) * 8 + 4 + (it & 3)];
-        }
-      }
       auto put_x = [&](int r, int it, uint32_t x1, uint32_t x2) {
         const uint32_t o = (uint32_t)r * p.x_row_bytes + (uint32_t)(it - item_begin) * 8u;
         sts64(x_base + (o >> 7) * 256u + (o & 127u), prmt(x1, x2, 0x5410u), prmt(x1, x2, 0x7632u));
       };
-#pragma unroll
-      for (int i = 0; i < kPre; ++i) {
-        const int it = item_begin + (int)threadIdx.x + i * kConsumerThreads;
-        if (it < item_end) put_x(0, it, px1[i], px2[i]);  // zeros beyond k
-      }
       for (int r = 0; r < p.m; ++r) {
         const uint32_t* xr = reinterpret_cast<const uint32_t*>(p.x + (int64_t)r * p.k);
-        for (int it = item_begin + (int)threadIdx.x + (r == 0 ? kPre * kConsumerThreads : 0); it < item_end;
-             it += kConsumerThreads) {
+        for (int it = item_begin + (int)threadIdx.x; it < item_end; it += kConsumerThreads) {
           const int t = it >> 2, pp = it & 3;
           const bool ok = it < item_valid_end;
           put_x(r, it, ok ? xr[t * 8 + pp] : 0u, ok ? xr[t * 8 + 4 + pp] : 0u);
@@ -581,6 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     }
     cluster.sync();  // keep remote shared memory alive until rank 0 has read it
   }
+#ifdef TG_W4_TRACE
   if (threadIdx.x == 0) {
     trace_stamp(p, 12);
     if (p.trace != nullptr) {
@@ -589,6 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
       p.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 15] = smid;
     }
   }
+#endif
 }
 
 }  // namespace

@@ -150,12 +150,18 @@ __device__ __forceinline__ void l2_prefetch_line(const void* src) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
 }
 
+// phase tracing is compiled in only with -DTG_W4_TRACE (scripts/trace_kernel.py builds that variant)
 __device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
+#ifdef TG_W4_TRACE
   if (p.trace != nullptr) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     p.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = t;
   }
+#else
+  (void)p;
+  (void)slot;
+#endif
 }
 
 template <tg_dtype DT>

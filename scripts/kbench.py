@@ -26,9 +26,16 @@ def main():
         layers = [synth_layer(n, k, 10 + i, dev) for i in range(copies)]
         x = torch.randn(1, k, device=dev).bfloat16()
 
+        side_a = os.environ.get("KB_SIDE", "B") == "A"
+        if side_a:  # same bytes read as the A int4 layout (ik = 4), LUT/scales per (padded) row as before
+            layers = [(w.view(n // 16, k // 64, 32, 4), lut, sz) for w, lut, sz in layers]
+
         def step():
             for w, lut, sz in layers:
-                op(x, w, G, sz, lut, True)
+                if side_a:
+                    op(w, x, G, sz, lut, False)
+                else:
+                    op(x, w, G, sz, lut, True)
 
         for _ in range(3):
             step()
@@ -48,7 +55,7 @@ def main():
         out[n] = round(us, 2)
         del layers
         torch.cuda.empty_cache()
-    print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("TG_W4")}, "l2x": os.environ.get("KB_L2X", "2.6"), "us_per_gemv": out,
+    print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("TG_W4")}, "side": os.environ.get("KB_SIDE", "B"), "l2x": os.environ.get("KB_L2X", "2.6"), "us_per_gemv": out,
                       "GBps": {n: round(algorithmic_bytes(n, n) / us / 1e3) for n, us in out.items()}}))
 
 
