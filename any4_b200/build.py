@@ -32,7 +32,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
     "-I", INCLUDE,
-]
+] + os.environ.get("TG_NVCC_EXTRA", "").split()  # e.g. -DTG_W4_TRACE for scripts/trace_kernel.py
 
 CAPI_LIB = os.path.join(LIB, "libtinygemm_b200.so")
 OPS_LIB = os.path.join(LIB, "tinygemm_ops.so")

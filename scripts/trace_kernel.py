@@ -1,5 +1,7 @@
 #!/usr/bin/env python
 """In-kernel phase timeline of the hot GEMV (debug tool; uses the tg_debug_set_trace hook).
+Needs the library built with tracing compiled in:  TG_NVCC_EXTRA=-DTG_W4_TRACE python -m any4_b200.build -f
+(and a plain `python -m any4_b200.build -f` afterwards).
 Prints, per phase, the median / p10 / p90 over CTAs of the time since the FIRST CTA started."""
 import ctypes
 import json
