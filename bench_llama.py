@@ -126,21 +126,32 @@ def main():
 
     tgf.set_static_weights(True)
     lib = _native.capi()
+    def note(msg):
+        if os.environ.get("LLAMA_DEBUG"):
+            print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     with torch.no_grad():
+        note("building model")
         model = Llama(dev, rank, world, args.ctx, args.layers)
+        note("model built")
         tok = torch.tensor([1], device=dev)
         lib.tg_reset_launch_count()
         logits = model(tok)
+        torch.cuda.synchronize()
+        note("first forward done")
         launches = int(lib.tg_launch_count())
         assert torch.isfinite(logits.float()).all(), "synthetic model produced non-finite logits"
         for _ in range(args.warmup):
             model(tok)
         torch.cuda.synchronize()
+        note("warm-up done, capturing")
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             out = model(tok)
+        note("captured")
         g.replay()
         torch.cuda.synchronize()
+        note("first replay done")
         if dist is not None:
             dist.barrier()
         sampler = ClockSampler(local) if rank == 0 else None
@@ -156,6 +167,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         clocks = sampler.stop() if sampler else None
+        del g, out  # a live CUDA graph holding NCCL kernels keeps destroy_process_group() from returning
+        torch.cuda.synchronize()
     if rank == 0:
         per_layer = 2 * any4_bytes(HID, HID) + 2 * any4_bytes(KV_HEADS * HEAD_DIM, HID) + 2 * any4_bytes(INTER, HID) + any4_bytes(HID, INTER)
         quant_bytes = per_layer * args.layers
