@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
 
       if (threadIdx.x < 128) {
         if (p.splits == 1) {
-          if (tj < nj && trow < rows_valid) p.y[(int64_t)tj * p.y_stride + row0 + trow] = f32_to_dt<DT>(total);
+          if (tj < nj && trow < rows_valid) store_y(p, (int64_t)tj * p.y_stride + row0 + trow, f32_to_dt<DT>(total));
         } else {
           exch[tj * 32 + trow] = total;  // one row block per CTA when k is split: exchanged after the loop
         }
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     if (cluster.block_rank() == 0 && threadIdx.x < 128 && tj < nj) {
       float sum = 0.f;
       for (unsigned r = 0; r < (unsigned)p.splits; ++r) sum += cluster.map_shared_rank(part, r)[tj * 32 + trow];
-      if (trow < rows_valid) p.y[(int64_t)tj * p.y_stride + row0 + trow] = f32_to_dt<DT>(sum);
+      if (trow < rows_valid) store_y(p, (int64_t)tj * p.y_stride + row0 + trow, f32_to_dt<DT>(sum));
     }
     cluster.sync();  // keep remote shared memory alive until rank 0 has read it
   }
@@ -645,10 +645,12 @@ int launch_m(Params p, int row_blocks, int64_t rows_x, const uint16_t* x, uint16
   // activation rows are processed in passes of up to 4 (bounded by the staging area)
   const int cap = kMaxXBytes / p.x_row_bytes;  // >= 1 by the choice of `splits`
   const int per_pass = cap < 4 ? cap : 4;
+  const Params peers0 = p;
   for (int64_t r0 = 0; r0 < rows_x; r0 += per_pass) {
     p.m = (int)((rows_x - r0) < per_pass ? (rows_x - r0) : per_pass);
     p.x = x + r0 * p.k;
     p.y = y + r0 * p.y_stride;
+    for (int r = 0; r < p.n_peer; ++r) p.y_peer[r] = peers0.y_peer[r] + r0 * p.y_stride;
     int rc = (p.m == 1) ? launch_one<DT, IK, true>(p, row_blocks, st) : launch_one<DT, IK, false>(p, row_blocks, st);
     if (rc != TG_OK) return rc;
   }
@@ -671,8 +673,11 @@ int launch_ik(const Params& p, int ik, int row_blocks, int64_t rows_x, const uin
 
 int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
                         const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
-                        tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st) {
+                        tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st,
+                        void* const* y_peers, int n_peers, int64_t y_row_stride) {
   Params p{};
+  p.n_peer = n_peers;
+  for (int r = 0; r < n_peers; ++r) p.y_peer[r] = static_cast<uint16_t*>(y_peers[r]);
   p.w = reinterpret_cast<const uint8_t*>(w);
   p.sz = (fmt == TG_W4_MX4) ? nullptr : reinterpret_cast<const uint32_t*>(sz);
   p.exps = (fmt == TG_W4_MX4) ? exps : nullptr;
@@ -680,7 +685,7 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
   p.k = (int)k;
   p.glog2 = group == 32 ? 5 : group == 64 ? 6 : group == 128 ? 7 : 8;
   p.tile_stride = 4 * k;
-  p.y_stride = w_rows;
+  p.y_stride = n_peers > 0 ? y_row_stride : w_rows;
 
   if (fmt == TG_W4_ANY4_GLOBAL || fmt == TG_W4_ANY4_ROWWISE) {
     p.lut = reinterpret_cast<const uint16_t*>(lut);

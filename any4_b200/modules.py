@@ -160,6 +160,32 @@ class Any4Linear(_PackedLinear):
         return super().extra_repr() + f", per_row={self.per_row}"
 
 
+class _SymmWorkspace:
+    """One peer-mapped (symmetric-memory) output workspace per (process group, device): two alternating m x n buffers
+    every rank can store into directly.  Shared by all RowShardedLinear layers of the process."""
+
+    _cache = {}
+
+    def __init__(self, group, device, dtype, m_cap, n_cap):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.m_cap, self.n_cap = m_cap, n_cap
+        self.buf = symm.empty((2, m_cap, n_cap), dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.turn = 0
+
+    @classmethod
+    def get(cls, group, device, dtype, m, n):
+        key = (id(group), str(device), dtype)
+        ws = cls._cache.get(key)
+        if ws is None or ws.m_cap < m or ws.n_cap < n:
+            ws = cls(group, device, dtype, max(m, 16 if ws is None else ws.m_cap), max(n, 0 if ws is None else ws.n_cap))
+            cls._cache[key] = ws
+        return ws
+
+
 class RowShardedLinear(torch.nn.Module):
     """Row-wise (output-feature) shard of a packed quantized Linear across the ranks of one node
     (BASELINE.json north_star: "weights shard row-wise across the 8 GPUs of one box
@@ -171,10 +197,20 @@ class RowShardedLinear(torch.nn.Module):
     local n/R outputs into its slice of a zero-filled m x n buffer and sums the buffers with ONE
     all-reduce: every element is value + 0 + ... + 0, so the result is bit-identical to the
     single-GPU output.
+
+    `fused=True` (B200-native path, weight-on-the-right 4-bit kernels): no collective kernel at all.  The GEMV's
+    epilogue stores this rank's n/R outputs straight into EVERY rank's copy of a symmetric-memory m x n buffer over
+    NVLink (include/tinygemm_b200.h: tg_gemm_w4_rm_sharded); one symmetric-memory barrier on the stream then
+    orders the readers behind all ranks' stores.  Bit-identical to the all-reduce path (same values, no sums).
+    `max_features` sizes the shared workspace (largest out_features of any sharded layer in the process).
     """
 
-    def __init__(self, full: _PackedLinear, rank: int, world: int, group=None):
+    def __init__(self, full: _PackedLinear, rank: int, world: int, group=None, fused: bool = False,
+                 max_features: int = 0):
         super().__init__()
+        self.fused = bool(fused) and world > 1 and full.kernel in (
+            "linear_y_f16RM_x_f16RM_W_any4TC", "linear_y_f16RM_x_f16RM_W_int4TC")
+        self.max_features = max(max_features, full.out_features)
         if not full.weight_reshaped:
             raise ValueError("pack the weight (reshape_weight) before sharding it")
         n = full.out_features
@@ -208,6 +244,11 @@ class RowShardedLinear(torch.nn.Module):
 
         lead = input.shape[:-1]
         x2d = input.view(-1, input.shape[-1])
+        if self.fused:
+            y = self._forward_fused(x2d)
+            if self.bias is not None:
+                y = y + self.bias
+            return y.reshape(*lead, self.out_features)
         y_local = self.local._gemm(x2d)
         full = torch.zeros((x2d.shape[0], self.out_features), device=x2d.device, dtype=x2d.dtype)
         full[:, self.lo:self.hi] = y_local[:, : self.hi - self.lo]
@@ -216,3 +257,30 @@ class RowShardedLinear(torch.nn.Module):
         if self.bias is not None:
             full = full + self.bias
         return full.view(*lead, self.out_features)
+
+    def _forward_fused(self, x2d):
+        import ctypes
+
+        from . import _native
+
+        loc = self.local
+        m, n = x2d.shape[0], self.out_features
+        ws = _SymmWorkspace.get(self.group, x2d.device, x2d.dtype, m, self.max_features)
+        turn = ws.turn
+        ws.turn ^= 1
+        elt = x2d.element_size()
+        base = (turn * ws.m_cap * ws.n_cap + self.lo) * elt   # this shard's first column in buffer `turn`
+        peers = (ctypes.c_void_p * self.world)(*[p + base for p in ws.ptrs])
+        is_any4 = hasattr(loc, "lut")
+        fmt = (2 if loc.lut.dim() == 2 else 1) if is_any4 else 0  # tg_w4_format
+        lib = _native.capi()
+        rc = lib.tg_gemm_w4_rm_sharded(
+            peers, self.world, ws.n_cap, ctypes.c_void_p(x2d.data_ptr()), ctypes.c_void_p(loc.weight.data_ptr()),
+            ctypes.c_void_p(loc.scales_and_zeros.data_ptr()),
+            ctypes.c_void_p(loc.lut.data_ptr()) if is_any4 else None, None,
+            m, self.hi - self.lo, x2d.shape[1], loc.group_size, loc.weight.shape[3] * 2, fmt,
+            0 if x2d.dtype == torch.bfloat16 else 1, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RuntimeError(_native.last_error())
+        ws.hdl.barrier(channel=0)   # all ranks' stores have landed before anyone reads the buffer
+        return ws.buf[turn, :m, :n]

@@ -237,7 +237,8 @@ def run_ours(args):
             w, lut, sz = synth_layer(n, k, 1234 + i, dev)
             lin.weight.data, lin.lut.data, lin.scales_and_zeros.data = w, lut, sz
             lin.weight_reshaped = True
-            layers.append(RowShardedLinear(lin, rank, world) if world > 1 else lin)
+            layers.append(RowShardedLinear(lin, rank, world, fused=args.exchange == "fused", max_features=11008)
+                          if world > 1 else lin)
         return layers
 
     def bench_shape(n, k, steps, warmup, with_e2e):
@@ -354,7 +355,9 @@ def run_ours(args):
                 "launch": "eager" if args.no_graph else "one CUDA graph per step (replayed K times)",
                 "l2_policy": f"inputs larger than L2: {head['copies']} distinct weight sets = "
                              f"{head['copies'] * nbytes / 1e6:.0f} MB rotated every step",
-                "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world} + NCCL all-reduce on y",
+                "parallelism": "1 GPU" if world == 1 else (
+                    f"row-sharded x{world}, exchange fused into the GEMV epilogue (peer stores over NVLink + barrier)"
+                    if args.exchange == "fused" else f"row-sharded x{world} + NCCL all-reduce on y"),
                 "other_shapes": {f"{e['n']}x{e['k']}": {"GBps": round(e["gbps"], 1), "us_per_gemv": round(e["us_per_gemv"], 3),
                                                          "frac_of_peak": round(e["gbps"] / world / peak, 4)} for e in extra},
             },
@@ -384,6 +387,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: 'fused' = GEMV epilogue stores into all ranks' symmetric buffers + one barrier; "
+                         "'nccl' = zero-padded all-reduce")
     ap.add_argument("--no-sweep", action="store_true", help="skip the informational format / m sweep")
     ap.add_argument("--profile-shape", type=int, default=0, help="(for ncu) run only the n=k=N GEMV set")
     args = ap.parse_args()

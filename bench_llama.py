@@ -35,7 +35,11 @@ def any4_bytes(n, k):
     return n * k // 2 + (k // G) * n * 4 + n * 32
 
 
-def make_linear(n, k, seed, dev, rank, world):
+_FUSED = True
+
+
+def make_linear(n, k, seed, dev, rank, world, fused=None):
+    fused = _FUSED if fused is None else fused
     from any4_b200.modules import Any4Linear, RowShardedLinear
 
     lin = Any4Linear(k, n, bias=False, device=dev, dtype=torch.bfloat16, group_size=G)
@@ -43,7 +47,7 @@ def make_linear(n, k, seed, dev, rank, world):
     # keep activations tame through 32 random layers: centre the per-group zero, small scales
     lin.weight.data, lin.lut.data, lin.scales_and_zeros.data = w, lut, sz * 0.25
     lin.weight_reshaped = True
-    return RowShardedLinear(lin, rank, world) if world > 1 else lin
+    return RowShardedLinear(lin, rank, world, fused=fused, max_features=INTER) if world > 1 else lin
 
 
 class Block(torch.nn.Module):
@@ -110,6 +114,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--ctx", type=int, default=128)
     ap.add_argument("--layers", type=int, default=LAYERS)
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -132,6 +137,8 @@ def main():
 
     with torch.no_grad():
         note("building model")
+        global _FUSED
+        _FUSED = args.exchange == "fused"
         model = Llama(dev, rank, world, args.ctx, args.layers)
         note("model built")
         tok = torch.tensor([1], device=dev)
@@ -181,7 +188,7 @@ def main():
             "ms_per_token": ms, "steps": args.steps, "warmup": args.warmup, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "Llama-3-8B any4 g=128 single-token decode, batch 1 (BASELINE configs[2]/[4])",
                        "layers": args.layers, "kv_context": args.ctx, "launch": "one CUDA graph per token",
-                       "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world}, NCCL all-reduce per Linear",
+                       "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world}, exchange per Linear: {args.exchange}",
                        "lm_head": "bf16 (not quantized, as in the reference)"},
             "bytes_per_token_per_gpu": total,
             "roofline": {"bound": "hbm", "achieved": total / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

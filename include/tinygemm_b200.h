@@ -134,6 +134,18 @@ int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_z
                   const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
                   int inner_k_tiles, tg_w4_format format, tg_weight_side side, tg_dtype dtype, void* stream);
 
+/* Row-sharded multi-GPU variant of the B-layout 4-bit GEMV with the exchange FUSED into the epilogue (no
+ * counterpart in the reference, which is single-GPU).  This rank holds `w_rows` consecutive weight
+ * rows of an n-row layer; `y_peers[r]` is the address, in rank r's copy of a symmetric (peer-mapped) m x n output
+ * buffer, of THIS shard's first column, and `y_row_stride` = n.  The kernel's epilogue stores the shard's outputs
+ * straight into every rank's buffer over NVLink - there is no separate all-gather / all-reduce kernel.  The caller
+ * orders the consumers of the buffer behind all ranks' stores (e.g. a symmetric-memory barrier on the stream) and
+ * must not reuse a buffer while a peer may still read it (alternate two buffers).  n_peers <= 8. */
+int tg_gemm_w4_rm_sharded(void* const* y_peers, int n_peers, int64_t y_row_stride, const void* x, const int32_t* w,
+                          const void* scales_zeros, const void* lut, const uint8_t* exponents, int64_t rows_x,
+                          int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_w4_format format, tg_dtype dtype,
+                          void* stream);
+
 /* int8.  replaces tinygemm_y_f16RM_x_f16RM_w_int8TC (TinyGemm_int8.cu:215-399, :430-457).
  *   inner_k_tiles B layout: 1, 2, 4;  A layout: 1, 2 */
 int tg_gemm_w8_rm(void* y, const void* x, const int32_t* w, const void* scales_zeros, int64_t rows_x,

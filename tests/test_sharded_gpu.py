@@ -43,6 +43,11 @@ def _worker(rank, world, port, q):
         want = full(x)
         got = RowShardedLinear(full, rank, world)(x)
         ok = ok and torch.equal(got, want)
+        # fused epilogue exchange over symmetric memory: no collective kernel, same bits
+        fused = RowShardedLinear(full, rank, world, fused=True, max_features=4096)
+        for _ in range(3):  # alternates the two workspace buffers
+            got_f = fused(x)
+            ok = ok and torch.equal(got_f, want)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
