@@ -48,6 +48,7 @@ def test_argument_validation_without_gpu(lib):
     assert w4(w_rows=60) == -1
     assert w4(fmt=3, dt=1, group=32) == -3   # mx4 is bf16 only (TG_ERR_UNSUPPORTED)
     assert w4(rows_x=0) == 0         # empty activation: nothing to launch
+    assert lib.tg_set_option(0, 1) == 0 and lib.tg_set_option(1, 0) == 0 and lib.tg_set_option(9, 1) == -1
     assert lib.tg_gemm_tc_workspace_bytes(16, 64, 256) >= 16 * 256 * 2 + 16 * 64 * 2
 
 

@@ -70,3 +70,44 @@ def test_capi_is_stream_ordered_and_graph_capturable(cuda_device):
     torch.cuda.synchronize()
     assert torch.equal(y_g, ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(x, w2, 128, sz, lut, True))
     assert not torch.equal(y_g, eager)
+
+
+def test_pdl_and_static_weights_keep_stream_order(cuda_device):
+    """TG_OPT_PDL / TG_OPT_STATIC_WEIGHTS must not change results: a chain of GEMVs whose activations are produced
+    by the previous kernel (the decode pattern) gives the same bits with every option combination."""
+    import tinygemm  # noqa: F401
+    from any4_b200 import _native
+
+    lib = _native.capi()
+    dev = cuda_device
+    ops = torch.ops.tinygemm
+    n = k = 1024
+    layers = []
+    for i in range(6):
+        case = dict(kind="gemm", fmt="any4r", dt="bf16", side="right", api="RM", m=1, n=n, k=k, g=128, ik=4, x_ik=1, seed=900 + i)
+        inp = C.make_inputs(case)
+        layers.append((ops.convert_matrix_to_m16n8k16_Bint4_layout(inp["codes"].to(dev), 4), inp["sz"].to(dev), inp["lut"].to(dev)))
+    x0 = torch.randn(1, k, generator=torch.Generator().manual_seed(1)).bfloat16().to(dev)
+
+    def chain():
+        x = x0
+        for w, sz, lut in layers:
+            y = ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(x, w, 128, sz, lut, True)
+            x = torch.tanh(y)  # a non-tinygemm kernel in between, and the next GEMV reads its output
+            x = ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(x, w, 128, sz, lut, True)  # GEMV straight after GEMV
+            x = torch.tanh(x)
+        return x
+
+    results = []
+    try:
+        for pdl, static in ((0, 0), (1, 0), (1, 1)):
+            assert lib.tg_set_option(0, pdl) == 0 and lib.tg_set_option(1, static) == 0
+            for _ in range(3):
+                results.append(chain().clone())
+            torch.cuda.synchronize()
+    finally:
+        lib.tg_set_option(0, 1)
+        lib.tg_set_option(1, 0)
+    for r in results[1:]:
+        assert torch.equal(r, results[0])
+    assert lib.tg_set_option(7, 1) == -1
