@@ -305,12 +305,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_a_kernel(const Params p) 
           const uint32_t xc = x_base + (uint32_t)(c - chunk_begin) * 512u;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const uint4 wv = lds128(sbase + GeoA<IK>::unit_off(u));
+            // ik = 4: a lane's four units are the four k-slots q of its pair, 64 B apart between pairs, so the 8
+            // lanes of a quarter-warp hit only 2 bank groups (4-way conflict).  Lanes that share an operand
+            // column (same lane & 3) must walk the units in the same order, but the order may differ between
+            // columns: rotating by (lane & 3) >> 1 halves the conflict, and since only the k-slot (hence the x
+            // offset) depends on the unit the rotation costs nothing.
+            const int ur = (IK == 4) ? ((u + ((lane & 3) >> 1)) & 3) : u;
+            const uint4 wv = lds128(sbase + (IK == 4 ? ur * 16 : GeoA<IK>::unit_off(u)));
             const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint32_t w = ww[i];
-              const int q = GeoA<IK>::q(u, i);
+              const int q = (IK == 4) ? ur : GeoA<IK>::q(u, i);
               const int tl = GeoA<IK>::tile(0, u, i);  // tile within this lane's half (0..3)
               // activation carriers read the word of THEIR half: tile = xsub*4 + tl
               const uint32_t xo = xc + (uint32_t)xsub * 256u + (uint32_t)(tl * 32 + q * 8);

@@ -327,6 +327,17 @@ def run_ours(args):
         wa = [w.view(n // 16, k // 64, 32, 4) for w, _, _ in ws]       # same bytes viewed as the A int4 layout (ik = 4)
         out["m1"]["int4_g128_A_layout(Int4Linear default)"] = timed(
             lambda: [ops.tinygemm_y_f16RM_x_f16RM_w_int4TC(w, x, G, sz, False) for w, (_, _, sz) in zip(wa, ws)])
+        # int8 and 16-bit weights (fragment-order kernel, untuned): 8 weight sets are enough to exceed L2 for 16-bit
+        w8 = [torch.randint(-2**31, 2**31 - 1, (n // 8, k // 64, 32, 4), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+              for _ in range(16)]
+        w16 = [torch.randn(n // 8, k // 32, 32, 8, generator=gen, device=dev).bfloat16() for _ in range(8)]
+        sz0 = ws[0][2]
+        copies_saved = copies
+        copies = 16
+        out["m1"]["int8_g128_B_layout"] = timed(lambda: [ops.tinygemm_y_f16RM_x_f16RM_w_int8TC(x, w, G, sz0, True) for w in w8])
+        copies = 8
+        out["m1"]["bf16_weights_B_layout"] = timed(lambda: [ops.tinygemm_y_f16RM_x_f16RM_w_f16TC(x, w, True) for w in w16])
+        copies = copies_saved
         out["unit"] = "us per GEMM at n=k=4096, bf16, CUDA graph, weights rotated through > 2.5x L2"
         return out
 
