@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+LIB_DIR = os.environ.get("ANY4_B200_LIB_DIR") or os.path.join(_HERE, "lib")  # override: A/B-testing two builds
 CAPI_PATH = os.path.join(LIB_DIR, "libtinygemm_b200.so")
 OPS_PATH = os.path.join(LIB_DIR, "tinygemm_ops.so")
 
@@ -57,7 +57,8 @@ def capi():
     for name in ("tg_convert_to_Aint4", "tg_convert_to_Aint8", "tg_convert_to_Bint4", "tg_convert_to_Bint8"):
         getattr(lib, name).argtypes = [vp, vp, i64, i64, i32, vp]
     lib.tg_gemm_w4_rm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, i32, vp]
-    lib.tg_gemm_w4_rm_sharded.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
+    if hasattr(lib, "tg_gemm_w4_rm_sharded"):  # (absent only in older builds loaded through ANY4_B200_LIB_DIR)
+        lib.tg_gemm_w4_rm_sharded.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
     lib.tg_gemm_w8_rm.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
     lib.tg_gemm_w16_rm.argtypes = [vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
     lib.tg_gemm_tc_workspace_bytes.argtypes = [i64, i64, i64]
@@ -67,6 +68,8 @@ def capi():
     lib.tg_gemm_w16_tc.argtypes = [vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp]
     lib.tg_dequant_int4.argtypes = [vp, vp, i64, vp]
     for name in CAPI_SYMBOLS:
+        if not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)
         if name.startswith(("tg_convert", "tg_gemm_w", "tg_dequant")):
             fn.restype = i32

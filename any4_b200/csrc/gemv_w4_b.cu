@@ -151,8 +151,8 @@ __device__ __noinline__ void slow_rows(const Params p, int row0, int rows_valid,
 // through one ring, so a block's table / scale staging and the previous block's epilogue hide under the
 // stream instead of costing a full kernel prologue + pipeline fill per 32 rows.
 // ---------------------------------------------------------------------------------------
-template <tg_dtype DT, int IK, bool M1>
-__global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) {
+template <tg_dtype DT, int IK, bool M1, bool PEERS>
+__device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& peers) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t dyn_base = smem_u32(smem_raw);
 
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
 
       if (threadIdx.x < 128) {
         if (p.splits == 1) {
-          if (tj < nj && trow < rows_valid) store_y(p, (int64_t)tj * p.y_stride + row0 + trow, f32_to_dt<DT>(total));
+          if (tj < nj && trow < rows_valid) store_y<PEERS>(p, peers, (int64_t)tj * p.y_stride + row0 + trow, f32_to_dt<DT>(total));
         } else {
           exch[tj * 32 + trow] = total;  // one row block per CTA when k is split: exchanged after the loop
         }
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
     if (cluster.block_rank() == 0 && threadIdx.x < 128 && tj < nj) {
       float sum = 0.f;
       for (unsigned r = 0; r < (unsigned)p.splits; ++r) sum += cluster.map_shared_rank(part, r)[tj * 32 + trow];
-      if (trow < rows_valid) store_y(p, (int64_t)tj * p.y_stride + row0 + trow, f32_to_dt<DT>(sum));
+      if (trow < rows_valid) store_y<PEERS>(p, peers, (int64_t)tj * p.y_stride + row0 + trow, f32_to_dt<DT>(sum));
     }
     cluster.sync();  // keep remote shared memory alive until rank 0 has read it
   }
@@ -576,6 +576,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) 
 #endif
 }
 
+template <tg_dtype DT, int IK, bool M1>
+__global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_kernel(const Params p) {
+  gemv_w4_b_body<DT, IK, M1, false>(p, Peers{});
+}
+// row-sharded variant: the epilogue stores into every rank's symmetric output buffer
+template <tg_dtype DT, int IK, bool M1>
+__global__ void __launch_bounds__(kThreads, 1) gemv_w4_b_peer_kernel(const Params p, const __grid_constant__ Peers peers) {
+  gemv_w4_b_body<DT, IK, M1, true>(p, peers);
+}
+
 }  // namespace
 namespace w4 {
 bool g_pdl = true;             // tg_set_option: programmatic dependent launch
@@ -586,11 +596,13 @@ int g_flags_env = -1;          // TG_W4_FLAGS (tuning / debug), read once
 namespace {
 
 template <tg_dtype DT, int IK, bool M1>
-int launch_one(const Params& p, int row_blocks, cudaStream_t st) {
+int launch_one(const Params& p, const Peers& peers, int row_blocks, cudaStream_t st) {
   auto kern = gemv_w4_b_kernel<DT, IK, M1>;
+  auto kern_peer = gemv_w4_b_peer_kernel<DT, IK, M1>;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(kern_peer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBytes) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(smem=%u) failed: %s", kDynSmemBytes, cudaGetErrorString(cudaGetLastError()));
       return TG_ERR_CUDA;
     }
@@ -630,7 +642,7 @@ int launch_one(const Params& p, int row_blocks, cudaStream_t st) {
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, pp);
+  cudaError_t e = peers.n > 0 ? cudaLaunchKernelEx(&cfg, kern_peer, pp, peers) : cudaLaunchKernelEx(&cfg, kern, pp);
   if (e != cudaSuccess) {
     set_error("gemv_w4_b launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -641,29 +653,30 @@ int launch_one(const Params& p, int row_blocks, cudaStream_t st) {
 }
 
 template <tg_dtype DT, int IK>
-int launch_m(Params p, int row_blocks, int64_t rows_x, const uint16_t* x, uint16_t* y, cudaStream_t st) {
+int launch_m(Params p, const Peers& peers0, int row_blocks, int64_t rows_x, const uint16_t* x, uint16_t* y,
+             cudaStream_t st) {
   // activation rows are processed in passes of up to 4 (bounded by the staging area)
   const int cap = kMaxXBytes / p.x_row_bytes;  // >= 1 by the choice of `splits`
   const int per_pass = cap < 4 ? cap : 4;
-  const Params peers0 = p;
+  Peers peers = peers0;
   for (int64_t r0 = 0; r0 < rows_x; r0 += per_pass) {
     p.m = (int)((rows_x - r0) < per_pass ? (rows_x - r0) : per_pass);
     p.x = x + r0 * p.k;
     p.y = y + r0 * p.y_stride;
-    for (int r = 0; r < p.n_peer; ++r) p.y_peer[r] = peers0.y_peer[r] + r0 * p.y_stride;
-    int rc = (p.m == 1) ? launch_one<DT, IK, true>(p, row_blocks, st) : launch_one<DT, IK, false>(p, row_blocks, st);
+    for (int r = 0; r < peers0.n; ++r) peers.y[r] = peers0.y[r] + r0 * p.y_stride;
+    int rc = (p.m == 1) ? launch_one<DT, IK, true>(p, peers, row_blocks, st) : launch_one<DT, IK, false>(p, peers, row_blocks, st);
     if (rc != TG_OK) return rc;
   }
   return TG_OK;
 }
 
 template <tg_dtype DT>
-int launch_ik(const Params& p, int ik, int row_blocks, int64_t rows_x, const uint16_t* x, uint16_t* y,
-              cudaStream_t st) {
+int launch_ik(const Params& p, const Peers& peers, int ik, int row_blocks, int64_t rows_x, const uint16_t* x,
+              uint16_t* y, cudaStream_t st) {
   switch (ik) {
-    case 2: return launch_m<DT, 2>(p, row_blocks, rows_x, x, y, st);
-    case 4: return launch_m<DT, 4>(p, row_blocks, rows_x, x, y, st);
-    case 8: return launch_m<DT, 8>(p, row_blocks, rows_x, x, y, st);
+    case 2: return launch_m<DT, 2>(p, peers, row_blocks, rows_x, x, y, st);
+    case 4: return launch_m<DT, 4>(p, peers, row_blocks, rows_x, x, y, st);
+    case 8: return launch_m<DT, 8>(p, peers, row_blocks, rows_x, x, y, st);
   }
   set_error("B-layout int4 innerKTiles must be 2, 4 or 8 (got %d)", ik);
   return TG_ERR_INVALID_ARGUMENT;
@@ -676,8 +689,9 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
                         tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st,
                         void* const* y_peers, int n_peers, int64_t y_row_stride) {
   Params p{};
-  p.n_peer = n_peers;
-  for (int r = 0; r < n_peers; ++r) p.y_peer[r] = static_cast<uint16_t*>(y_peers[r]);
+  Peers peers{};
+  peers.n = n_peers;
+  for (int r = 0; r < n_peers; ++r) peers.y[r] = static_cast<uint16_t*>(y_peers[r]);
   p.w = reinterpret_cast<const uint8_t*>(w);
   p.sz = (fmt == TG_W4_MX4) ? nullptr : reinterpret_cast<const uint32_t*>(sz);
   p.exps = (fmt == TG_W4_MX4) ? exps : nullptr;
@@ -720,8 +734,8 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
   p.x_row_bytes = p.chunks_per_split * 256;  // one split's activations, whole 128-k chunks
 
   if (dt == TG_BF16)
-    return launch_ik<TG_BF16>(p, ik, row_blocks, rows_x, (const uint16_t*)x, (uint16_t*)y, st);
-  return launch_ik<TG_FP16>(p, ik, row_blocks, rows_x, (const uint16_t*)x, (uint16_t*)y, st);
+    return launch_ik<TG_BF16>(p, peers, ik, row_blocks, rows_x, (const uint16_t*)x, (uint16_t*)y, st);
+  return launch_ik<TG_FP16>(p, peers, ik, row_blocks, rows_x, (const uint16_t*)x, (uint16_t*)y, st);
 }
 
 }  // namespace tg

@@ -52,8 +52,6 @@ struct Params {
   int glog2;             // log2(group)
   int64_t tile_stride;   // bytes between consecutive n-tiles of the packed weight = 4 * k
   int64_t y_stride;      // elements between activation rows of y (= total w_rows; the full row for a row shard)
-  uint16_t* y_peer[8];   // row-sharded mode: the same output location in every rank's symmetric buffer (incl. ours);
-  int n_peer;            //   the epilogue stores the shard's outputs to all of them over NVLink (0 = plain y)
   int x_row_bytes;       // staged bytes per activation row, multiple of 256 (whole 128-k chunks)
   int splits;            // cluster size along k (gridDim.y)
   int chunks_per_split;  // ceil(ceil(k / 128) / splits)       } precomputed on the host: no integer
@@ -152,13 +150,20 @@ __device__ __forceinline__ void l2_prefetch_line(const void* src) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
 }
 
-// output store: local, or replicated into every peer's buffer (peer pointers are ordinary UVA addresses)
-__device__ __forceinline__ void store_y(const Params& p, int64_t idx, uint16_t v) {
-  if (p.n_peer == 0) {
-    p.y[idx] = v;
-  } else {
+// Row-sharded mode (separate kernel argument so that the single-GPU kernels keep their exact parameter block):
+// the same output location in every rank's symmetric buffer (ours included); the epilogue stores the shard's
+// outputs to all of them over NVLink (peer pointers are ordinary UVA addresses).
+struct Peers {
+  uint16_t* y[8];
+  int n;
+};
+template <bool PEERS>
+__device__ __forceinline__ void store_y(const Params& p, const Peers& peers, int64_t idx, uint16_t v) {
+  if constexpr (PEERS) {
 #pragma unroll 1
-    for (int r = 0; r < p.n_peer; ++r) p.y_peer[r][idx] = v;
+    for (int r = 0; r < peers.n; ++r) peers.y[r][idx] = v;
+  } else {
+    p.y[idx] = v;
   }
 }
 
