@@ -62,6 +62,8 @@ struct Geo<4> {  // slice = [2 super-tiles][32 lanes][2 words]; row g at +g*32 i
   __device__ static constexpr int tp(int u, int i) { return (u >> 1) * 2 + (i & 1); }
   // words i and i + 2 use the same tile pair and adjacent k-slots: their activations are 16 contiguous bytes
   static constexpr int kXPartner = 2;
+  static constexpr int kStagger = 16;  // see tile_off(): rows 32 B apart, the partner tile fills the other 16-byte halves
+  __device__ static int swz(int u, int) { return u; }
 };
 template <>
 struct Geo<2> {  // slice = [4 super-tiles][32 lanes][1 word]; row g at +g*16 inside each 128 B
@@ -70,6 +72,8 @@ struct Geo<2> {  // slice = [4 super-tiles][32 lanes][1 word]; row g at +g*16 in
   __device__ static constexpr int q(int, int i) { return i; }
   __device__ static constexpr int tp(int u, int) { return u; }
   static constexpr int kXPartner = 1;  // words (0,1) and (2,3) are adjacent k-slots of one tile pair
+  static constexpr int kStagger = 64;  // rows 16 B apart: four rows fill 64 B, the partner tile the other 64
+  __device__ static int swz(int u, int) { return u; }
 };
 template <>
 struct Geo<8> {  // slice = [1 super-tile][32 lanes][4 words]; row g at +g*64
@@ -78,7 +82,25 @@ struct Geo<8> {  // slice = [1 super-tile][32 lanes][4 words]; row g at +g*64
   __device__ static constexpr int q(int u, int) { return u; }
   __device__ static constexpr int tp(int, int i) { return i; }
   static constexpr int kXPartner = 0;  // each word is a different tile pair: no 16-byte pairing
+  // rows 64 B apart: lanes with k-slot id (lane & 3) >= 2 take their units one step ahead, so four rows of a tile
+  // cover slots {u, u+4, u+1, u+5} (16-byte slots mod 128 B) and the partner tile, 32 B further, the other four.
+  // The order may only depend on lane & 3: lanes with equal lane & 3 share the activation operand of an mma.
+  static constexpr int kStagger = 32;
+  __device__ static int swz(int u, int lane) { return (u + ((lane >> 1) & 1)) & 3; }
 };
+
+// Shared-memory bank conflicts of the 16-byte weight loads: a quarter-warp (8 lanes) is served per wavefront, and 8
+// rows of ONE n-tile sit 16*IK/2 bytes apart, so rows j and j+4 collide.  Hence (a) lane L owns row
+// row_of_lane(L) = L with bits 2 and 3 swapped: a quarter-warp then holds rows 4h..4h+3 of TWO tiles, and (b) the
+// odd tile of each pair is staged kStagger bytes further, which puts its rows into the banks the even tile leaves free.
+__device__ __forceinline__ int row_of_lane(int l) { return (l & 0x13) | ((l & 4) << 1) | ((l & 8) >> 1); }
+template <int IK>
+__device__ __forceinline__ uint32_t tile_off_t(int t) {
+  return (uint32_t)t * kTileStageBytes + (uint32_t)((t + 1) >> 1) * Geo<IK>::kStagger;
+}
+constexpr uint32_t kStageBytesB = kStageBytes + 256u;             // room for the staggers, keeps stages 128-B aligned
+constexpr uint32_t kDynSmemBytesB = kDynSmemBytes + (kStages + 1) * 256u;
+static_assert(kDynSmemBytesB <= 232448u, "exceeds the 227 KiB opt-in shared memory of sm_100");
 
 // ---------------------------------------------------------------------------------------
 // Exact per-row fallback, taken only when a CTA produced a non-finite sum.  The block-structured
@@ -179,18 +201,21 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
   const int n_groups = p.k >> p.glog2;
 
   // ---- shared memory carve-up (window addresses, see the constants above) ----
+  // full barriers come in halves: [s][0] covers the first 1024 k of stage s (chunks of warps 0..7), [s][1] the rest
+  // (warps 8..15), so that half of the warps start on the first 16 KiB of the stream instead of the first 32
   const uint32_t full_bar = dyn_base;
-  const uint32_t empty_bar = dyn_base + 8u * kStages;
+  const uint32_t empty_bar = dyn_base + 16u * kStages;
   const uint32_t low_base = dyn_base + kCtrlBytes;
   const uint32_t table_base = (low_base + 0xffffu) & ~0xffffu;
   const uint32_t x_base = table_base + 128u;
   const uint32_t high_base = table_base + kTableBytes;
-  const int n_low = min(kStages, (int)((table_base - low_base) / kStageBytes));
-  const uint32_t sz_base = high_base + (uint32_t)(kStages - n_low) * kStageBytes;
+  const int n_low = min(kStages, (int)((table_base - low_base) / kStageBytesB));
+  const uint32_t sz_base = high_base + (uint32_t)(kStages - n_low) * kStageBytesB;
   const uint32_t red_base = sz_base + kSzBytes;
   auto stage_addr = [&](int s) -> uint32_t {
-    return s < n_low ? low_base + (uint32_t)s * kStageBytes : high_base + (uint32_t)(s - n_low) * kStageBytes;
+    return s < n_low ? low_base + (uint32_t)s * kStageBytesB : high_base + (uint32_t)(s - n_low) * kStageBytesB;
   };
+  auto tile_off = [](int t) -> uint32_t { return tile_off_t<IK>(t); };
 
   // group scale/zero words of this CTA's k range (the host picks `splits` so that they fit kSzBytes)
   const int group_first = (chunk_begin * kChunkK) >> p.glog2;
@@ -210,19 +235,23 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
       const int k0 = c0 * kChunkK;
       const int kvalid = min(min(kStageK, (chunk_end - c0) * kChunkK), p.k - k0);
       const uint32_t bytes = (uint32_t)kvalid * 4u;  // per n-tile: 8 rows * kvalid / 2
-      const uint32_t bar = full_bar + s * 8;
-      mbar_expect_tx(bar, bytes * (uint32_t)tiles_valid);
+      const uint32_t bytes0 = min(bytes, 4096u), bytes1 = bytes - bytes0;
+      const uint32_t bar = full_bar + s * 16;
+      mbar_expect_tx(bar, bytes0 * (uint32_t)tiles_valid);
+      mbar_expect_tx(bar + 8, bytes1 * (uint32_t)tiles_valid);  // 0 bytes: the phase completes right away
       const uint32_t dst = stage_addr(s);
-      for (int t = 0; t < tiles_valid; ++t) {
-        // 4 KiB bulk copies: the size class that sustains full HBM rate (scripts/microbench/stream_bw.cu)
-        for (uint32_t o = 0; o < bytes; o += 4096u)
-          bulk_g2s(dst + t * kTileStageBytes + o, wsrc + t * p.tile_stride + (int64_t)k0 * 4 + o, min(4096u, bytes - o),
-                   bar, pol);
-      }
+      // 4 KiB bulk copies: the size class that sustains full HBM rate (scripts/microbench/stream_bw.cu); the
+      // first k half of all four tiles is requested before the second
+      for (int t = 0; t < tiles_valid; ++t)
+        bulk_g2s(dst + tile_off(t), wsrc + t * p.tile_stride + (int64_t)k0 * 4, bytes0, bar, pol);
+      if (bytes1)
+        for (int t = 0; t < tiles_valid; ++t)
+          bulk_g2s(dst + tile_off(t) + 4096u, wsrc + t * p.tile_stride + (int64_t)k0 * 4 + 4096, bytes1, bar + 8, pol);
     };
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
-        mbar_init(full_bar + s * 8, 1);
+        mbar_init(full_bar + s * 16, 1);
+        mbar_init(full_bar + s * 16 + 8, 1);
         mbar_init(empty_bar + s * 8, kWarps);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -245,7 +274,7 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
           // only when (almost) everything has.  Requesting the rest once stage 0 is here gets the consumers
           // going ~1 us earlier, and they need > 1 us for a stage anyway.
           if (jj == 1) {
-            if (p.flags & 1) mbar_wait(full_bar, 0u);
+            if (p.flags & 1) mbar_wait(full_bar + 8, 0u);
             trace_stamp(p, 3);
           }
           if (jj >= kStages) mbar_wait(empty_bar + (jj % kStages) * 8, (uint32_t)(jj / kStages - 1) & 1u);
@@ -273,13 +302,13 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
     uint32_t psz[kPreSz];
     auto load_sz_word = [&](int row0, int i) -> uint32_t {  // word i = (group i / 32, row i % 32) of a row block
       const int gi = group_first + (i >> 5);
-      const int row = min(row0 + (i & 31), p.w_rows - 1);
+      const int row = min(row0 + row_of_lane(i & 31), p.w_rows - 1);  // staged in lane order
       if (is_mx4) return e8m0_to_dt<DT>((uint32_t)p.exps[(int64_t)row * n_groups + gi]) | 0x80000000u;  // zero = -0
       return p.sz[(int64_t)gi * p.w_rows + row];
     };
     auto load_block_regs = [&](int rb) {
       const int row0 = rb * kRowsPerCta;
-      const int row = min(row0 + lane, p.w_rows - 1);
+      const int row = min(row0 + row_of_lane(lane), p.w_rows - 1);
       const uint16_t* lrow = p.lut + (int64_t)row * p.lut_stride;
       lut0 = *reinterpret_cast<const uint4*>(lrow);
       lut1 = *reinterpret_cast<const uint4*>(lrow + 8);
@@ -358,13 +387,15 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
     const bool has_row23 = M1 ? false : (set1 ? p.m > 2 : p.m > 3);
     const uint32_t xa01 = (x_active && has_row01) ? 1u : 0u;
     const uint32_t xa23 = (x_active && has_row23) ? 1u : 0u;
-    const uint32_t w_lane_off = (uint32_t)(lane >> 3) * kTileStageBytes + (uint32_t)warp * kTileChunkBytes +
-                                (uint32_t)(lane & 7) * Geo<IK>::kRowStride;
+    const int rlane = row_of_lane(lane);  // the weight row (within the block) this lane owns
+    const uint32_t w_lane_off = tile_off(rlane >> 3) + (uint32_t)warp * kTileChunkBytes +
+                                (uint32_t)(rlane & 7) * Geo<IK>::kRowStride;
     uint32_t xr0[4] = {0u, 0u, 0u, 0u}, xr1[4] = {0u, 0u, 0u, 0u};  // x fragments (stay zero on inactive lanes)
     uint32_t xs0[4] = {0u, 0u, 0u, 0u}, xs1[4] = {0u, 0u, 0u, 0u};  // rows mi+2 (!M1)
     constexpr int kChains = 2;            // independent HMMA accumulation chains
     const int nj = M1 ? 1 : p.m;
-    const int tj = threadIdx.x >> 5, trow = threadIdx.x & 31;
+    const int tj = threadIdx.x >> 5, trow = threadIdx.x & 31;  // epilogue thread (tj, trow) owns y[tj][row0 + trow]
+    const int tlane = row_of_lane(trow);                       // the lane that owns row trow (the swap is an involution)
     float* const exch = reinterpret_cast<float*>(smem_raw + kExchOff);
 
     int jj = 0;  // stage counter across row blocks (ring position / parity)
@@ -407,9 +438,10 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
 
         // one lane per warp polls (512 threads spinning on try_wait would compete with the TMA writes for the
         // shared-memory pipe); after the warp-level sync every lane observes the completed phase itself
-        if (lane == 0) mbar_wait(full_bar + s * 8, (uint32_t)(jj / kStages) & 1u);
+        const uint32_t my_full = full_bar + s * 16 + (warp >> 3) * 8;
+        if (lane == 0) mbar_wait(my_full, (uint32_t)(jj / kStages) & 1u);
         __syncwarp();
-        while (!mbar_try(full_bar + s * 8, (uint32_t)(jj / kStages) & 1u)) {
+        while (!mbar_try(my_full, (uint32_t)(jj / kStages) & 1u)) {
         }
         if (threadIdx.x == 0 && jj < 4) trace_stamp(p, 6 + jj);
         // A chunk is always processed whole: beyond k the staged activations are zero, so whatever bytes the
@@ -420,14 +452,15 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
           const uint32_t xc = x_base + (uint32_t)(c - chunk_begin) * 512u + x_lane_off;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const uint4 wv = lds128(sbase + Geo<IK>::unit_off(u));
+            const int uu = Geo<IK>::swz(u, lane);  // this lane's u-th unit (bank-conflict-free order for ik = 8)
+            const uint4 wv = lds128(sbase + Geo<IK>::unit_off(uu));
             const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
             if constexpr (M1) {
               // activations of the unit's four words: 16-byte loads where two words are adjacent in x
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const uint32_t xo_i = xc + (uint32_t)((Geo<IK>::tp(u, i) >> 1) * 256 + (Geo<IK>::tp(u, i) & 1) * 64 +
-                                                      Geo<IK>::q(u, i) * 8);
+                                                      Geo<IK>::q(uu, i) * 8);
                 constexpr int P = Geo<IK>::kXPartner;
                 if constexpr (P == 0) {
                   lds64_if(xr0[i], xr1[i], xo_i, x_active);
@@ -438,8 +471,8 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int q = Geo<IK>::q(u, i);
-              const int tp = Geo<IK>::tp(u, i);
+              const int q = Geo<IK>::q(uu, i);
+              const int tp = Geo<IK>::tp(u, i);  // == tp(uu, i) whenever swz is not the identity (ik = 8: tp = i)
               const uint32_t w = ww[i];
               // byte0: tile 2tp (k0, k0+8)   byte2: tile 2tp (k0+1, k0+9)
               // byte1: tile 2tp+1 (k0, k0+8) byte3: tile 2tp+1 (k0+1, k0+9)
@@ -507,14 +540,14 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
           if (tj == 0) {
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) {
-              total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)trow * 4u));
-              total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)(32 + trow) * 4u));
+              total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)tlane * 4u));
+              total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)(32 + tlane) * 4u));
             }
           }
         } else {
 #pragma unroll
           for (int w = 0; w < kWarps; ++w)
-            total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)(tj * 32 + trow) * 4u));
+            total += __uint_as_float(lds32(red_base + (uint32_t)w * 512u + (uint32_t)(tj * 32 + tlane) * 4u));
         }
       }
       // next block's table and group words (their loads were issued during the last stage)
@@ -601,9 +634,9 @@ int launch_one(const Params& p, const Peers& peers, int row_blocks, cudaStream_t
   auto kern_peer = gemv_w4_b_peer_kernel<DT, IK, M1>;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBytes) != cudaSuccess ||
-        cudaFuncSetAttribute(kern_peer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBytes) != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem=%u) failed: %s", kDynSmemBytes, cudaGetErrorString(cudaGetLastError()));
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBytesB) != cudaSuccess ||
+        cudaFuncSetAttribute(kern_peer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBytesB) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%u) failed: %s", kDynSmemBytesB, cudaGetErrorString(cudaGetLastError()));
       return TG_ERR_CUDA;
     }
     attr_set = true;
@@ -624,7 +657,7 @@ int launch_one(const Params& p, const Peers& peers, int row_blocks, cudaStream_t
   pp.blk_r = row_blocks % gx;
   cfg.gridDim = dim3((unsigned)gx, (unsigned)p.splits, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = kDynSmemBytes;
+  cfg.dynamicSmemBytes = kDynSmemBytesB;
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   int na = 0;

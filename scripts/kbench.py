@@ -19,32 +19,36 @@ def main():
     dev = torch.device("cuda:0")
     op = torch.ops.tinygemm.tinygemm_y_f16RM_x_f16RM_w_any4TC
     out = {}
+    checks = {}
     for n in [int(a) for a in sys.argv[1:]] or [4096, 8192, 11008]:
         k = n
         nbytes = algorithmic_bytes(n, k)
         copies = max(3, int(float(os.environ.get('KB_L2X', '2.6')) * 126e6 / nbytes) + 1)
         layers = [synth_layer(n, k, 10 + i, dev) for i in range(copies)]
-        x = torch.randn(1, k, device=dev).bfloat16()
+        x = torch.randn(int(os.environ.get('KB_M', '1')), k, device=dev).bfloat16()
 
         side_a = os.environ.get("KB_SIDE", "B") == "A"
         if side_a:  # same bytes read as the A int4 layout (ik = 4), LUT/scales per (padded) row as before
             layers = [(w.view(n // 16, k // 64, 32, 4), lut, sz) for w, lut, sz in layers]
 
         def step():
-            for w, lut, sz in layers:
-                if side_a:
-                    op(w, x, G, sz, lut, False)
-                else:
-                    op(x, w, G, sz, lut, True)
+            return [op(w, x, G, sz, lut, False) if side_a else op(x, w, G, sz, lut, True) for w, lut, sz in layers]
 
         for _ in range(3):
             step()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            step()
+            outs = step()
         g.replay()
         torch.cuda.synchronize()
+        # the graph's results (static weights + PDL, back to back) must equal plain stream-ordered launches bit for bit
+        tgf.set_static_weights(False)
+        _native_lib.tg_set_option(0, 0)
+        ok = all(torch.equal(a, b) for a, b in zip(outs, step()))
+        tgf.set_static_weights(os.environ.get('KB_STATIC', '1') == '1')
+        _native_lib.tg_set_option(0, int(os.environ.get('KB_PDL', '1')))
+        checks[n] = ok
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
@@ -53,9 +57,9 @@ def main():
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / (10 * copies)
         out[n] = round(us, 2)
-        del layers
+        del layers, outs, g
         torch.cuda.empty_cache()
-    print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("TG_W4")}, "side": os.environ.get("KB_SIDE", "B"), "l2x": os.environ.get("KB_L2X", "2.6"), "us_per_gemv": out,
+    print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("TG_W4")}, "side": os.environ.get("KB_SIDE", "B"), "m": int(os.environ.get("KB_M", "1")), "l2x": os.environ.get("KB_L2X", "2.6"), "us_per_gemv": out, "bit_equal_to_plain_launches": checks,
                       "GBps": {n: round(algorithmic_bytes(n, n) / us / 1e3) for n, us in out.items()}}))
 
 
