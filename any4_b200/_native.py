@@ -25,6 +25,7 @@ CAPI_SYMBOLS = (
     "tg_gemm_w4_rm", "tg_gemm_w4_rm_sharded", "tg_gemm_w8_rm", "tg_gemm_w16_rm",
     "tg_gemm_tc_workspace_bytes", "tg_gemm_w4_tc", "tg_gemm_w8_tc", "tg_gemm_w16_tc",
     "tg_dequant_int4",
+    "tg_decode_add_rmsnorm", "tg_decode_silu_mul", "tg_decode_rope_attention",
 )
 
 
@@ -67,11 +68,16 @@ def capi():
     lib.tg_gemm_w8_tc.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, i32, vp, vp]
     lib.tg_gemm_w16_tc.argtypes = [vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp]
     lib.tg_dequant_int4.argtypes = [vp, vp, i64, vp]
+    if hasattr(lib, "tg_decode_add_rmsnorm"):
+        f32 = ctypes.c_float
+        lib.tg_decode_add_rmsnorm.argtypes = [vp, vp, vp, vp, i64, f32, i32, vp]
+        lib.tg_decode_silu_mul.argtypes = [vp, vp, i64, i32, vp]
+        lib.tg_decode_rope_attention.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp]
     for name in CAPI_SYMBOLS:
         if not hasattr(lib, name):
             continue
         fn = getattr(lib, name)
-        if name.startswith(("tg_convert", "tg_gemm_w", "tg_dequant")):
+        if name.startswith(("tg_convert", "tg_gemm_w", "tg_dequant", "tg_decode")):
             fn.restype = i32
     _capi = lib
     return lib
@@ -84,6 +90,13 @@ def load_ops():
         return
     import torch
 
+    other = os.environ.get("ANY4_B200_OPS_LIB")
+    if other:
+        # benchmarking aid (bench_llama.py --impl reference): register ANOTHER implementation of the same 19
+        # `tinygemm::` schemas - the unmodified reference extension - under this package's Python layer
+        torch.ops.load_library(other)
+        _ops_loaded = True
+        return
     if not os.path.exists(OPS_PATH):
         raise _missing(OPS_PATH)
     capi()  # make sure the dependency is resolvable even without the rpath

@@ -497,7 +497,7 @@ int launch_gemm_w4_rm_A(void* y, const void* x, const int32_t* w, const void* sz
   while (splits < 8 && row_blocks * splits * 2 <= 148 && chunks / (splits * 2) >= kWarps) splits *= 2;
   auto fits = [&](int sp) {
     const int64_t cps = div_up(chunks, sp);
-    const int64_t groups = cps * kChunkK / group + 2;
+    const int64_t groups = group <= kChunkK ? cps * (kChunkK / group) : cps * kChunkK / group + 2;  // exact / bound
     return cps * 256 <= kMaxXBytes && groups * 128 <= (int64_t)kSzBytes;
   };
   while (splits < 8 && !fits(splits)) ++splits;

@@ -1,0 +1,75 @@
+"""Decode-step plumbing around the quantized GEMVs: thin torch-tensor wrappers over the
+`tg_decode_*` entry points of the C ABI (csrc/decode_ops.cu).  Single token, bf16 / fp16, CUDA only; launches go
+to the current stream and are CUDA-graph capturable.  There is no CPU fallback.
+
+The reference has no counterpart: its benchmark.py:145-146 times the stock HF model around the tinygemm ops.
+"""
+import ctypes
+
+import torch
+
+from . import _native
+
+_DT = {torch.bfloat16: 0, torch.float16: 1}
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(_native.last_error())
+
+
+def _req(t, name):
+    if not (t.is_cuda and t.is_contiguous() and t.dtype in _DT):
+        raise RuntimeError(f"{name} must be a contiguous CUDA bf16/fp16 tensor")
+
+
+def add_rmsnorm(h, delta, weight, eps, out=None):
+    """h += delta (in place, rounded; delta may be None); returns rmsnorm(h, eps) * weight."""
+    _req(h, "h"), _req(weight, "weight")
+    if delta is not None:
+        _req(delta, "delta")
+        if delta.numel() != h.numel() or delta.dtype != h.dtype:
+            raise RuntimeError("delta must match h")
+    if weight.numel() != h.numel() or weight.dtype != h.dtype:
+        raise RuntimeError("weight must match h")
+    out = torch.empty_like(h) if out is None else out
+    _check(_native.capi().tg_decode_add_rmsnorm(_p(h), _p(delta), _p(weight), _p(out), h.numel(), float(eps),
+                                                _DT[h.dtype], _stream()))
+    return out
+
+
+def silu_mul(gate_up, out=None):
+    """gate_up = [gate | up] (2n values, e.g. the output of a fused gate/up GEMV) -> silu(gate) * up, n values."""
+    _req(gate_up, "gate_up")
+    n = gate_up.numel() // 2
+    out = torch.empty(gate_up.shape[:-1] + (n,), device=gate_up.device, dtype=gate_up.dtype) if out is None else out
+    _check(_native.capi().tg_decode_silu_mul(_p(gate_up), _p(out), n, _DT[gate_up.dtype], _stream()))
+    return out
+
+
+def rope_attention(qkv, cos, sin, k_cache, v_cache, pos, n_heads, n_kv_heads, head_dim=128, scale=None, out=None):
+    """qkv = [q | k | v] of ONE token: rotary embedding of q and k, append k, v at `pos` to the caches
+    [n_kv_heads][cache_len][head_dim], attention over positions 0..pos -> [n_heads * head_dim]."""
+    for t, nm in ((qkv, "qkv"), (cos, "cos"), (sin, "sin"), (k_cache, "k_cache"), (v_cache, "v_cache")):
+        _req(t, nm)
+    if qkv.numel() != (n_heads + 2 * n_kv_heads) * head_dim:
+        raise RuntimeError("qkv has the wrong size")
+    if cos.numel() != head_dim or sin.numel() != head_dim:
+        raise RuntimeError("cos / sin must have head_dim elements")
+    cache_len = k_cache.numel() // (n_kv_heads * head_dim)
+    if v_cache.numel() != k_cache.numel() or k_cache.numel() != n_kv_heads * cache_len * head_dim:
+        raise RuntimeError("k_cache / v_cache must be [n_kv_heads][cache_len][head_dim]")
+    scale = head_dim ** -0.5 if scale is None else scale
+    out = torch.empty(qkv.shape[:-1] + (n_heads * head_dim,), device=qkv.device, dtype=qkv.dtype) if out is None else out
+    _check(_native.capi().tg_decode_rope_attention(_p(qkv), _p(cos), _p(sin), _p(k_cache), _p(v_cache), _p(out), n_heads,
+                                                   n_kv_heads, head_dim, int(pos), cache_len, float(scale),
+                                                   _DT[qkv.dtype], _stream()))
+    return out

@@ -160,6 +160,40 @@ class Any4Linear(_PackedLinear):
         return super().extra_repr() + f", per_row={self.per_row}"
 
 
+def fuse_rows(linears):
+    """Concatenate packed quantized Linears that read the same input along the output-feature axis (q|k|v, gate|up):
+    ONE GEMV launch instead of several.  The row-tiled packed layouts concatenate along
+    dim 0; every output element is computed from the same products as by the separate layers (rows are independent):
+    bit-identical to torch.cat of the separate outputs whenever the launches use the same k-split, else equal up to the
+    order of the fp32 partial sums (tests/test_decode_gpu.py::test_fuse_rows).  All layers must be packed (`weight_reshaped`), of the
+    same class / kernel / group size / inner-k / dtype, with out_features a multiple of the tile height."""
+    first = linears[0]
+    tile = 8 if first._PACKERS.get(first.kernel, "").startswith("B") else 16
+    for lin in linears:
+        if type(lin) is not type(first) or not lin.weight_reshaped:
+            raise ValueError("fuse_rows needs packed layers of one class")
+        if (lin.in_features, lin.group_size, lin.kernel, lin.w_inner_k) != (
+                first.in_features, first.group_size, first.kernel, first.w_inner_k):
+            raise ValueError("fuse_rows: in_features / group_size / kernel / w_inner_k differ")
+        if lin.out_features % tile or (lin.bias is None) != (first.bias is None):
+            raise ValueError(f"fuse_rows: out_features must be multiples of {tile}, bias all-or-none")
+        if getattr(lin, "per_row", True) is not True:
+            raise ValueError("fuse_rows: a global LUT cannot be concatenated (use per_row=True)")
+    dev, dt = first.weight.device, first.scales_and_zeros.dtype
+    kw = dict(bias=first.bias is not None, device="meta", dtype=dt, group_size=first.group_size, kernel=first.kernel,
+              w_inner_k=first.w_inner_k)
+    fused = type(first)(first.in_features, sum(l.out_features for l in linears), **kw)
+    fused.weight = torch.nn.Parameter(torch.cat([l.weight.data for l in linears], 0), requires_grad=False)
+    fused.scales_and_zeros = torch.nn.Parameter(torch.cat([l.scales_and_zeros.data for l in linears], 1).contiguous())
+    if hasattr(first, "lut"):
+        fused.lut = torch.nn.Parameter(torch.cat([l.lut.data for l in linears], 0))
+    if first.bias is not None:
+        fused.bias = torch.nn.Parameter(torch.cat([l.bias.data for l in linears], 0))
+    fused.weight_reshaped = True
+    assert fused.weight.device == dev
+    return fused
+
+
 class _SymmWorkspace:
     """One peer-mapped (symmetric-memory) output workspace per (process group, device): two alternating m x n buffers
     every rank can store into directly.  Shared by all RowShardedLinear layers of the process."""

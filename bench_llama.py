@@ -51,6 +51,8 @@ def make_linear(n, k, seed, dev, rank, world, fused=None):
 
 
 class Block(torch.nn.Module):
+    """Stock plumbing: separate q/k/v/gate/up launches, torch ops for norm / rope / attention / activation."""
+
     def __init__(self, idx, dev, rank, world, ctx):
         super().__init__()
         s = 1000 * idx
@@ -87,21 +89,68 @@ class Block(torch.nn.Module):
         return h + self.down(F.silu(self.gate(x)) * self.up(x))
 
 
+class FusedBlock(torch.nn.Module):
+    """any4_b200 plumbing: q|k|v and gate|up as one GEMV each (modules.fuse_rows) and three
+    small PDL kernels (any4_b200.decode) - 8 launches per layer.  Same weights, same math as Block (the row-fused
+    GEMVs are bit-identical to the separate ones; the element-wise kernels mirror the framework's roundings)."""
+
+    def __init__(self, idx, dev, rank, world, ctx):
+        super().__init__()
+        from any4_b200.modules import RowShardedLinear, fuse_rows
+
+        s = 1000 * idx
+        mk = lambda n, k, seed: make_linear(n, k, seed, dev, rank, 1)  # noqa: E731  (shard after fusing)
+
+        def shard(lin, cap):
+            return RowShardedLinear(lin, rank, world, fused=_FUSED, max_features=cap) if world > 1 else lin
+
+        self.qkv = shard(fuse_rows([mk(HID, HID, s + 1), mk(KV_HEADS * HEAD_DIM, HID, s + 2),
+                                    mk(KV_HEADS * HEAD_DIM, HID, s + 3)]), 2 * INTER)
+        self.o = shard(mk(HID, HID, s + 4), 2 * INTER)
+        self.gate_up = shard(fuse_rows([mk(INTER, HID, s + 5), mk(INTER, HID, s + 6)]), 2 * INTER)
+        self.down = shard(mk(HID, INTER, s + 7), 2 * INTER)
+        self.n1 = torch.ones(HID, device=dev, dtype=torch.bfloat16)
+        self.n2 = torch.ones(HID, device=dev, dtype=torch.bfloat16)
+        gen = torch.Generator(device=dev).manual_seed(s + 9)
+        self.kc = torch.randn(1, KV_HEADS, ctx + 1, HEAD_DIM, device=dev, generator=gen).bfloat16()
+        self.vc = torch.randn(1, KV_HEADS, ctx + 1, HEAD_DIM, device=dev, generator=gen).bfloat16()
+        self.ctx = ctx
+
+    def forward(self, h, delta, cos, sin):
+        """h: residual stream (updated in place); delta: the previous layer's MLP output still to be added."""
+        from any4_b200 import decode as D
+
+        x = D.add_rmsnorm(h, delta, self.n1, EPS)
+        a = D.rope_attention(self.qkv(x), cos, sin, self.kc, self.vc, self.ctx, HEADS, KV_HEADS, HEAD_DIM)
+        x = D.add_rmsnorm(h, self.o(a), self.n2, EPS)
+        return self.down(D.silu_mul(self.gate_up(x)))
+
+
 class Llama(torch.nn.Module):
-    def __init__(self, dev, rank, world, ctx, layers):
+    def __init__(self, dev, rank, world, ctx, layers, fused_plumbing):
         super().__init__()
         gen = torch.Generator(device=dev).manual_seed(7)
+        self.fused_plumbing = fused_plumbing
         self.emb = (torch.randn(VOCAB, HID, device=dev, generator=gen) * 0.02).bfloat16()
-        self.blocks = torch.nn.ModuleList([Block(i, dev, rank, world, ctx) for i in range(layers)])
+        blk = FusedBlock if fused_plumbing else Block
+        self.blocks = torch.nn.ModuleList([blk(i, dev, rank, world, ctx) for i in range(layers)])
         self.norm = torch.ones(HID, device=dev, dtype=torch.bfloat16)
         self.lm_head = (torch.randn(VOCAB, HID, device=dev, generator=gen) * 0.02).bfloat16()
         pos = torch.tensor([float(ctx)], device=dev)
         inv = 1.0 / (THETA ** (torch.arange(0, HEAD_DIM, 2, device=dev).float() / HEAD_DIM))
         ang = torch.cat([pos[:, None] * inv[None], pos[:, None] * inv[None]], -1)
         self.cos, self.sin = ang.cos().bfloat16().view(1, 1, 1, HEAD_DIM), ang.sin().bfloat16().view(1, 1, 1, HEAD_DIM)
+        self.cos1, self.sin1 = self.cos.view(HEAD_DIM).contiguous(), self.sin.view(HEAD_DIM).contiguous()
 
     def forward(self, tok):
         h = self.emb[tok].view(1, HID)
+        if self.fused_plumbing:
+            from any4_b200 import decode as D
+
+            delta = None
+            for b in self.blocks:
+                delta = b(h, delta, self.cos1, self.sin1)
+            return F.linear(D.add_rmsnorm(h, delta, self.norm, EPS), self.lm_head)
         for b in self.blocks:
             h = b(h, self.cos, self.sin)
         return F.linear(F.rms_norm(h, (HID,), self.norm, EPS), self.lm_head)
@@ -115,6 +164,11 @@ def main():
     ap.add_argument("--ctx", type=int, default=128)
     ap.add_argument("--layers", type=int, default=LAYERS)
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
+    ap.add_argument("--plumbing", default="fused", choices=["fused", "torch"],
+                    help="fused: q|k|v and gate|up as one GEMV each + any4_b200.decode kernels; torch: stock ops")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"],
+                    help="reference: the same harness (torch plumbing) on the UNMODIFIED reference tinygemm kernels "
+                         "(oracle/_ref/tinygemm.so, recompiled for sm_100a); single GPU only")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -126,11 +180,22 @@ def main():
 
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
+    reference = args.impl == "reference"
+    if reference:
+        assert world == 1, "--impl reference is single-GPU"
+        ref_so = os.path.join(ROOT, "oracle", "_ref", "tinygemm.so")
+        if not os.path.exists(ref_so):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/tinygemm.so not built"}))
+            return
+        os.environ["ANY4_B200_OPS_LIB"] = ref_so  # any4_b200.modules / functional then drive the reference's ops
+        args.plumbing = "torch"
     from any4_b200 import _native
     from any4_b200 import functional as tgf
 
-    tgf.set_static_weights(True)
-    lib = _native.capi()
+    lib = None
+    if not reference:
+        tgf.set_static_weights(True)
+        lib = _native.capi()
     def note(msg):
         if os.environ.get("LLAMA_DEBUG"):
             print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
@@ -139,14 +204,15 @@ def main():
         note("building model")
         global _FUSED
         _FUSED = args.exchange == "fused"
-        model = Llama(dev, rank, world, args.ctx, args.layers)
+        model = Llama(dev, rank, world, args.ctx, args.layers, args.plumbing == "fused")
         note("model built")
         tok = torch.tensor([1], device=dev)
-        lib.tg_reset_launch_count()
+        if lib is not None:
+            lib.tg_reset_launch_count()
         logits = model(tok)
         torch.cuda.synchronize()
         note("first forward done")
-        launches = int(lib.tg_launch_count())
+        launches = int(lib.tg_launch_count()) if lib is not None else None
         assert torch.isfinite(logits.float()).all(), "synthetic model produced non-finite logits"
         for _ in range(args.warmup):
             model(tok)
@@ -185,15 +251,18 @@ def main():
         peak, src = measured_peak()
         print(json.dumps({
             "metric": "llama3_8b_any4_g128_decode_tok_per_s", "value": 1e3 / ms, "unit": "tok/s", "n_gpus": world,
+            "impl": "reference tinygemm kernels (recompiled sm_100a) in the same harness" if reference else "any4_b200",
             "ms_per_token": ms, "steps": args.steps, "warmup": args.warmup, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "Llama-3-8B any4 g=128 single-token decode, batch 1 (BASELINE configs[2]/[4])",
                        "layers": args.layers, "kv_context": args.ctx, "launch": "one CUDA graph per token",
                        "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world}, exchange per Linear: {args.exchange}",
+                       "plumbing": ("q|k|v and gate|up row-fused GEMVs + any4_b200.decode kernels (8 launches / layer)"
+                                    if args.plumbing == "fused" else "stock torch ops, 7 GEMV launches / layer"),
                        "lm_head": "bf16 (not quantized, as in the reference)"},
             "bytes_per_token_per_gpu": total,
             "roofline": {"bound": "hbm", "achieved": total / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": total / (ms * 1e-3) / 1e9 / peak, "peak_source": src + " (of measured)"},
-            "gemv_launches_per_token": launches, "clocks": clocks}))
+            "library_launches_per_token": launches, "clocks": clocks}))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -190,6 +190,24 @@ int tg_gemm_w16_tc(void* y, const void* x, const void* w, int64_t rows_x, int64_
  *   in [n_words] int32 -> out [n_words][8] bf16 */
 int tg_dequant_int4(const int32_t* in, void* out, int64_t n_words, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Decode-step plumbing around the GEMVs (no counterpart in tinygemm_lib - the
+ * reference leaves these to the HF model code its benchmark.py:145-146 times as a whole).  Single token,
+ * dtype = activation dtype, all kernels use programmatic dependent launch like the GEMVs (TG_OPT_PDL).
+ * ------------------------------------------------------------------------------------ */
+/* h[n] <- h + delta (delta may be NULL), rounded to dtype;  out[n] <- rmsnorm(h, eps) * weight[n]
+ * (fp32 statistics, one rounding).  n % 8 == 0, n <= 8192. */
+int tg_decode_add_rmsnorm(void* h, const void* delta, const void* weight, void* out, int64_t n, float eps,
+                          tg_dtype dtype, void* stream);
+/* out[n] <- silu(gate_up[0..n)) * gate_up[n..2n)  (output of a fused gate|up GEMV).  n % 8 == 0. */
+int tg_decode_silu_mul(const void* gate_up, void* out, int64_t n, tg_dtype dtype, void* stream);
+/* qkv = [n_heads*128 | n_kv_heads*128 | n_kv_heads*128] (output of a fused q|k|v GEMV): rotary embedding
+ * (half-rotation, cos/sin [128]) of q and k, append k, v to the caches [n_kv_heads][cache_len][128] at `pos`,
+ * attention of the token over positions 0..pos with GQA, out [n_heads*128].  head_dim must be 128, pos <= 512. */
+int tg_decode_rope_attention(const void* qkv, const void* cos, const void* sin, void* k_cache, void* v_cache,
+                             void* out, int n_heads, int n_kv_heads, int head_dim, int pos, int cache_len,
+                             float scale, tg_dtype dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
