@@ -25,7 +25,7 @@ CAPI_SYMBOLS = (
     "tg_gemm_w4_rm", "tg_gemm_w4_rm_sharded", "tg_gemm_w8_rm", "tg_gemm_w16_rm",
     "tg_gemm_tc_workspace_bytes", "tg_gemm_w4_tc", "tg_gemm_w8_tc", "tg_gemm_w16_tc",
     "tg_dequant_int4",
-    "tg_decode_add_rmsnorm", "tg_decode_silu_mul", "tg_decode_rope_attention",
+    "tg_decode_add_rmsnorm", "tg_decode_silu_mul", "tg_decode_rope_attention", "tg_gemm_w4_rm_silu_pairs",
 )
 
 
@@ -72,6 +72,7 @@ def capi():
         f32 = ctypes.c_float
         lib.tg_decode_add_rmsnorm.argtypes = [vp, vp, vp, vp, i64, f32, i32, vp]
         lib.tg_decode_silu_mul.argtypes = [vp, vp, i64, i32, vp]
+        lib.tg_gemm_w4_rm_silu_pairs.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
         lib.tg_decode_rope_attention.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp]
     for name in CAPI_SYMBOLS:
         if not hasattr(lib, name):

@@ -22,7 +22,7 @@ void set_w4_options(int pdl, int static_weights);
 int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
                         const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
                         tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st,
-                        void* const* y_peers = nullptr, int n_peers = 0, int64_t y_row_stride = 0);
+                        void* const* y_peers = nullptr, int n_peers = 0, int64_t y_row_stride = 0, int silu_pairs = 0);
 int launch_gemm_w4_rm_A(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
                         const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
                         tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st);
@@ -189,6 +189,35 @@ int tg_gemm_w4_rm_sharded(void* const* y_peers, int n_peers, int64_t y_row_strid
   }
   return launch_gemm_w4_rm_B(y_peers[0], x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
                              clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride);
+}
+
+int tg_gemm_w4_rm_silu_pairs(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
+                             const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
+                             int inner_k_tiles, tg_w4_format format, tg_dtype dtype, void* stream) {
+  const char* fn = "tg_gemm_w4_rm_silu_pairs";
+  int rc = check_common(fn, y, x, w, rows_x, w_rows, k, TG_WEIGHT_B, dtype);
+  if (rc != TG_OK) return rc;
+  TG_REQUIRE(format >= TG_W4_INT4 && format <= TG_W4_MX4, "%s: bad format", fn);
+  TG_REQUIRE(valid_group(group), "%s: qGroupSize must be 32, 64, 128 or 256 (got %d)", fn, group);
+  TG_REQUIRE(k % group == 0, "%s: k must be a multiple of qGroupSize", fn);
+  const int ik = inner_k_tiles;
+  TG_REQUIRE(ik == 2 || ik == 4 || ik == 8, "%s: B-layout innerKTiles must be 2, 4 or 8 (got %d)", fn, ik);
+  TG_REQUIRE((k / 16) % ik == 0, "%s: k/16 must be a multiple of innerKTiles", fn);
+  if (format == TG_W4_MX4) {
+    TG_REQUIRE(exponents != nullptr && dtype == TG_BF16, "%s: mx4 needs exponents and bf16", fn);
+  } else {
+    TG_REQUIRE(scales_zeros != nullptr && aligned16(scales_zeros), "%s: scales_zeros missing or misaligned", fn);
+  }
+  if (format == TG_W4_ANY4_GLOBAL || format == TG_W4_ANY4_ROWWISE)
+    TG_REQUIRE(lut != nullptr && aligned16(lut), "%s: any4 LUT missing or misaligned", fn);
+  if (rows_x == 0) return TG_OK;
+  const uint16_t* clut = nullptr;
+  if (format == TG_W4_INT4 || format == TG_W4_MX4) {
+    rc = const_lut_for(format, dtype, (cudaStream_t)stream, &clut);
+    if (rc != TG_OK) return rc;
+  }
+  return launch_gemm_w4_rm_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
+                             (cudaStream_t)stream, nullptr, 0, 0, /*silu_pairs=*/1);
 }
 
 int tg_gemm_w8_rm(void* y, const void* x, const int32_t* w, const void* scales_zeros, int64_t rows_x,

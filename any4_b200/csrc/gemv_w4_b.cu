@@ -572,7 +572,15 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
 
       if (threadIdx.x < 128) {
         if (p.splits == 1) {
-          if (tj < nj && trow < rows_valid) store_y<PEERS>(p, peers, (int64_t)tj * p.y_stride + row0 + trow, f32_to_dt<DT>(total));
+          if (p.flags & 16) {  // (gate, up) row pairs -> silu(gate) * up
+            const uint32_t mine = f32_to_dt<DT>(total);
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+            if (tj < nj && !(trow & 1) && trow < rows_valid)
+              store_y<PEERS>(p, peers, (int64_t)tj * p.y_stride + ((row0 + trow) >> 1),
+                             silu_mul_dt<DT>((uint16_t)mine, (uint16_t)other));
+          } else if (tj < nj && trow < rows_valid) {
+            store_y<PEERS>(p, peers, (int64_t)tj * p.y_stride + row0 + trow, f32_to_dt<DT>(total));
+          }
         } else {
           exch[tj * 32 + trow] = total;  // one row block per CTA when k is split: exchanged after the loop
         }
@@ -593,7 +601,15 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
     if (cluster.block_rank() == 0 && threadIdx.x < 128 && tj < nj) {
       float sum = 0.f;
       for (unsigned r = 0; r < (unsigned)p.splits; ++r) sum += cluster.map_shared_rank(part, r)[tj * 32 + trow];
-      if (trow < rows_valid) store_y<PEERS>(p, peers, (int64_t)tj * p.y_stride + row0 + trow, f32_to_dt<DT>(sum));
+      if (p.flags & 16) {
+        const uint32_t mine = f32_to_dt<DT>(sum);
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+        if (!(trow & 1) && trow < rows_valid)
+          store_y<PEERS>(p, peers, (int64_t)tj * p.y_stride + ((row0 + trow) >> 1),
+                         silu_mul_dt<DT>((uint16_t)mine, (uint16_t)other));
+      } else if (trow < rows_valid) {
+        store_y<PEERS>(p, peers, (int64_t)tj * p.y_stride + row0 + trow, f32_to_dt<DT>(sum));
+      }
     }
     cluster.sync();  // keep remote shared memory alive until rank 0 has read it
   }
@@ -720,7 +736,7 @@ int launch_ik(const Params& p, const Peers& peers, int ik, int row_blocks, int64
 int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
                         const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
                         tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st,
-                        void* const* y_peers, int n_peers, int64_t y_row_stride) {
+                        void* const* y_peers, int n_peers, int64_t y_row_stride, int silu_pairs) {
   Params p{};
   Peers peers{};
   peers.n = n_peers;
@@ -732,7 +748,7 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
   p.k = (int)k;
   p.glog2 = group == 32 ? 5 : group == 64 ? 6 : group == 128 ? 7 : 8;
   p.tile_stride = 4 * k;
-  p.y_stride = n_peers > 0 ? y_row_stride : w_rows;
+  p.y_stride = n_peers > 0 ? y_row_stride : silu_pairs ? w_rows / 2 : w_rows;
 
   if (fmt == TG_W4_ANY4_GLOBAL || fmt == TG_W4_ANY4_ROWWISE) {
     p.lut = reinterpret_cast<const uint16_t*>(lut);
@@ -763,7 +779,7 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
   p.splits = splits;
   p.trace = g_trace_buf;
   if (g_flags_env < 0) g_flags_env = getenv("TG_W4_FLAGS") ? atoi(getenv("TG_W4_FLAGS")) : 0;  // tuning knob
-  p.flags = g_flags_env | (g_static_weights ? 8 : 0);
+  p.flags = g_flags_env | (g_static_weights ? 8 : 0) | (silu_pairs ? 16 : 0);
   p.chunks_per_split = (int)div_up(chunks, splits);
   p.x_row_bytes = p.chunks_per_split * 256;  // one split's activations, whole 128-k chunks
 

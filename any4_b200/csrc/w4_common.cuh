@@ -57,7 +57,8 @@ struct Params {
   int chunks_per_split;  // ceil(ceil(k / 128) / splits)       } precomputed on the host: no integer
   int blk_q, blk_r;      // row_blocks / gridDim.x and % gridDim.x  } divisions on the kernel's critical start-up path
   int flags;             // bit 0: request the first stage alone (staged pipeline fill); bit 1 (debug): skip the
-                         // dequant/mma body (pure streaming); bit 3: weights/LUT/scales are static (PDL early start)
+                         // dequant/mma body (pure streaming); bit 3: weights/LUT/scales are static (PDL early start);
+                         // bit 4: weight rows (2j, 2j+1) = (gate_j, up_j), store silu(gate)*up to y[..][j]
   unsigned long long* trace;  // optional [CTAs][16] globaltimer stamps (debug, tg_debug_set_trace)
 };
 
@@ -215,6 +216,23 @@ __device__ __forceinline__ uint16_t f32_to_dt(float f) {
   } else {
     return __half_as_ushort(__float2half_rn(f));
   }
+}
+
+template <tg_dtype DT>
+__device__ __forceinline__ float dt_to_f32(uint16_t v) {
+  if constexpr (DT == TG_BF16) {
+    return __uint_as_float((uint32_t)v << 16);
+  } else {
+    return __half2float(__ushort_as_half(v));
+  }
+}
+// fused activation epilogue (Params::flags bit 4): silu(gate) * up on values already rounded to the activation
+// dtype, with the roundings of separate silu and mul kernels (== tg_decode_silu_mul on the plain GEMV's output)
+template <tg_dtype DT>
+__device__ __forceinline__ uint16_t silu_mul_dt(uint16_t gate, uint16_t up) {
+  const float g = dt_to_f32<DT>(gate);
+  const float s = dt_to_f32<DT>(f32_to_dt<DT>(g / (1.f + __expf(-g))));
+  return f32_to_dt<DT>(s * dt_to_f32<DT>(up));
 }
 
 // e8m0 -> dtype bits: 2^(e-127), 255 -> NaN (reference: Dequantization.cuh:331-351)

@@ -73,3 +73,23 @@ def rope_attention(qkv, cos, sin, k_cache, v_cache, pos, n_heads, n_kv_heads, he
                                                    n_kv_heads, head_dim, int(pos), cache_len, float(scale),
                                                    _DT[qkv.dtype], _stream()))
     return out
+
+
+def linear_silu_pairs(lin, x):
+    """`lin`: a packed Any4Linear (weight-on-the-right kernel, per-row LUT, no bias) whose rows interleave a gate and
+    an up projection (row 2j = gate_j, row 2j+1 = up_j, see modules.fuse_rows(..., interleave=True)); returns
+    silu(gate(x)) * up(x) [m][out_features / 2] from ONE launch (activation fused into the GEMV epilogue)."""
+    from .modules import Any4Linear
+
+    if not (isinstance(lin, Any4Linear) and lin.weight_reshaped and lin.per_row and lin.bias is None
+            and lin.kernel == "linear_y_f16RM_x_f16RM_W_any4TC"):
+        raise RuntimeError("linear_silu_pairs needs a packed per-row-LUT Any4Linear with the weight on the right, no bias")
+    _req(x, "x")
+    x2 = x.view(-1, x.shape[-1])
+    w = lin.weight
+    w_rows, ik = w.shape[0] * 8, w.shape[3] * 2
+    y = torch.empty(x2.shape[0], w_rows // 2, device=x.device, dtype=x.dtype)
+    _check(_native.capi().tg_gemm_w4_rm_silu_pairs(_p(y), _p(x2), _p(w), _p(lin.scales_and_zeros), _p(lin.lut), None,
+                                                   x2.shape[0], w_rows, x2.shape[1], lin.group_size, ik, 2,
+                                                   _DT[x.dtype], _stream()))
+    return y.view(*x.shape[:-1], w_rows // 2)

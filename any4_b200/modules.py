@@ -160,7 +160,7 @@ class Any4Linear(_PackedLinear):
         return super().extra_repr() + f", per_row={self.per_row}"
 
 
-def fuse_rows(linears):
+def fuse_rows(linears, interleave=False):
     """Concatenate packed quantized Linears that read the same input along the output-feature axis (q|k|v, gate|up):
     ONE GEMV launch instead of several.  The row-tiled packed layouts concatenate along
     dim 0; every output element is computed from the same products as by the separate layers (rows are independent):
@@ -168,6 +168,8 @@ def fuse_rows(linears):
     order of the fp32 partial sums (tests/test_decode_gpu.py::test_fuse_rows).  All layers must be packed (`weight_reshaped`), of the
     same class / kernel / group size / inner-k / dtype, with out_features a multiple of the tile height."""
     first = linears[0]
+    if interleave:
+        return _fuse_rows_interleaved(linears)
     tile = 8 if first._PACKERS.get(first.kernel, "").startswith("B") else 16
     for lin in linears:
         if type(lin) is not type(first) or not lin.weight_reshaped:
@@ -191,6 +193,33 @@ def fuse_rows(linears):
         fused.bias = torch.nn.Parameter(torch.cat([l.bias.data for l in linears], 0))
     fused.weight_reshaped = True
     assert fused.weight.device == dev
+    return fused
+
+
+def _fuse_rows_interleaved(linears):
+    """fuse_rows(..., interleave=True): rows alternate between the layers (row 2j = linears[0] row j, row 2j+1 =
+    linears[1] row j, ...), the form any4_b200.decode.linear_silu_pairs consumes for gate|up.  Row order inside the
+    packed tiles changes, so this works on UNPACKED layers (weight = [out][in] int32 codes) and packs the result."""
+    first, r = linears[0], len(linears)
+    for lin in linears:
+        if type(lin) is not type(first) or lin.weight_reshaped:
+            raise ValueError("interleaved fuse_rows needs unpacked layers of one class (call it before reshape_weight)")
+        if (lin.in_features, lin.out_features, lin.group_size, lin.kernel, lin.w_inner_k) != (
+                first.in_features, first.out_features, first.group_size, first.kernel, first.w_inner_k):
+            raise ValueError("interleaved fuse_rows: shapes / group_size / kernel / w_inner_k differ")
+        if lin.bias is not None or getattr(lin, "per_row", True) is not True:
+            raise ValueError("interleaved fuse_rows: no bias, per-row LUT only")
+    n, dt = first.out_features, first.scales_and_zeros.dtype
+    kw = dict(bias=False, device="meta", dtype=dt, group_size=first.group_size, kernel=first.kernel,
+              w_inner_k=first.w_inner_k)
+    fused = type(first)(first.in_features, r * n, **kw)
+    fused.weight = torch.nn.Parameter(
+        torch.stack([l.weight.data for l in linears], 1).reshape(r * n, first.in_features), requires_grad=False)
+    fused.scales_and_zeros = torch.nn.Parameter(
+        torch.stack([l.scales_and_zeros.data for l in linears], 2).reshape(-1, r * n, 2).contiguous())
+    if hasattr(first, "lut"):
+        fused.lut = torch.nn.Parameter(torch.stack([l.lut.data for l in linears], 1).reshape(r * n, -1).contiguous())
+    fused.reshape_weight(first.w_inner_k)
     return fused
 
 

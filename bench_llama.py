@@ -107,7 +107,11 @@ class FusedBlock(torch.nn.Module):
         self.qkv = shard(fuse_rows([mk(HID, HID, s + 1), mk(KV_HEADS * HEAD_DIM, HID, s + 2),
                                     mk(KV_HEADS * HEAD_DIM, HID, s + 3)]), 2 * INTER)
         self.o = shard(mk(HID, HID, s + 4), 2 * INTER)
-        self.gate_up = shard(fuse_rows([mk(INTER, HID, s + 5), mk(INTER, HID, s + 6)]), 2 * INTER)
+        # 1 GPU: gate and up rows interleaved (synthetic packed data: any row order is the same workload) so that
+        # silu(gate) * up happens in the GEMV epilogue; sharded: gate | up blocks + the separate silu*mul kernel
+        self.act_in_epilogue = world == 1
+        self.gate_up = (mk(2 * INTER, HID, s + 5) if self.act_in_epilogue else
+                        shard(fuse_rows([mk(INTER, HID, s + 5), mk(INTER, HID, s + 6)]), 2 * INTER))
         self.down = shard(mk(HID, INTER, s + 7), 2 * INTER)
         self.n1 = torch.ones(HID, device=dev, dtype=torch.bfloat16)
         self.n2 = torch.ones(HID, device=dev, dtype=torch.bfloat16)
@@ -123,7 +127,8 @@ class FusedBlock(torch.nn.Module):
         x = D.add_rmsnorm(h, delta, self.n1, EPS)
         a = D.rope_attention(self.qkv(x), cos, sin, self.kc, self.vc, self.ctx, HEADS, KV_HEADS, HEAD_DIM)
         x = D.add_rmsnorm(h, self.o(a), self.n2, EPS)
-        return self.down(D.silu_mul(self.gate_up(x)))
+        act = D.linear_silu_pairs(self.gate_up, x) if self.act_in_epilogue else D.silu_mul(self.gate_up(x))
+        return self.down(act)
 
 
 class Llama(torch.nn.Module):
@@ -256,7 +261,7 @@ def main():
             "config": {"workload": "Llama-3-8B any4 g=128 single-token decode, batch 1 (BASELINE configs[2]/[4])",
                        "layers": args.layers, "kv_context": args.ctx, "launch": "one CUDA graph per token",
                        "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world}, exchange per Linear: {args.exchange}",
-                       "plumbing": ("q|k|v and gate|up row-fused GEMVs + any4_b200.decode kernels (8 launches / layer)"
+                       "plumbing": ("q|k|v and gate|up row-fused GEMVs (silu*mul in the gate|up epilogue on 1 GPU) + any4_b200.decode kernels, 7-8 launches / layer"
                                     if args.plumbing == "fused" else "stock torch ops, 7 GEMV launches / layer"),
                        "lm_head": "bf16 (not quantized, as in the reference)"},
             "bytes_per_token_per_gpu": total,

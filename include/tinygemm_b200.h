@@ -201,6 +201,13 @@ int tg_decode_add_rmsnorm(void* h, const void* delta, const void* weight, void* 
                           tg_dtype dtype, void* stream);
 /* out[n] <- silu(gate_up[0..n)) * gate_up[n..2n)  (output of a fused gate|up GEMV).  n % 8 == 0. */
 int tg_decode_silu_mul(const void* gate_up, void* out, int64_t n, tg_dtype dtype, void* stream);
+/* tg_gemm_w4_rm (weight on the right, B layout) with the activation fused into the epilogue: the weight holds
+ * gate and up projections ROW-INTERLEAVED (row 2j = gate_j, row 2j+1 = up_j; w_rows even, padded rows come in
+ * pairs) and y [rows_x][w_rows/2] = silu(gate) * up.  Every intermediate is rounded exactly as by tg_gemm_w4_rm
+ * followed by tg_decode_silu_mul, so the result equals that two-kernel sequence. */
+int tg_gemm_w4_rm_silu_pairs(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
+                             const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
+                             int inner_k_tiles, tg_w4_format format, tg_dtype dtype, void* stream);
 /* qkv = [n_heads*128 | n_kv_heads*128 | n_kv_heads*128] (output of a fused q|k|v GEMV): rotary embedding
  * (half-rotation, cos/sin [128]) of q and k, append k, v to the caches [n_kv_heads][cache_len][128] at `pos`,
  * attention of the token over positions 0..pos with GQA, out [n_heads*128].  head_dim must be 128, pos <= 512. */

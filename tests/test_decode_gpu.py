@@ -122,3 +122,40 @@ def test_fuse_rows(rows):
         else:
             assert ((got.float() - want.float()).abs() <= 2.0 ** -7 * want.float().abs() + 1e-6).all()
             assert (got == want).float().mean() > 0.98
+
+
+@pytest.mark.parametrize("m", [1, 3])
+@pytest.mark.parametrize("n,k", [(4096, 4096), (512, 4096), (2048, 1024)])
+def test_linear_silu_pairs(m, n, k):
+    """gate|up row-interleaved + activation in the GEMV epilogue == separate GEMVs followed by silu * mul."""
+    import copy
+
+    from any4_b200 import decode as D
+    from any4_b200.modules import Any4Linear, fuse_rows
+
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(n + k + m)
+    lins = []
+    for _ in range(2):
+        lin = Any4Linear(k, n, bias=False, device=dev, dtype=torch.bfloat16, group_size=128)
+        lin.weight.data = torch.randint(0, 16, (n, k), device=dev, generator=g, dtype=torch.int32)
+        lin.lut.data = ((torch.rand(n, 16, device=dev, generator=g) * 15).sort(1).values.bfloat16() - 8)
+        lin.scales_and_zeros.data = torch.stack([torch.rand(k // 128, n, device=dev, generator=g) * 0.02 + 0.001,
+                                                 torch.randn(k // 128, n, device=dev, generator=g) * 0.02], 2).bfloat16()
+        lins.append(lin)
+    fused = fuse_rows([copy.deepcopy(l) for l in lins], interleave=True)
+    for lin in lins:
+        lin.reshape_weight(4)
+    x = torch.randn(m, k, device=dev, generator=g).bfloat16()
+    yg, yu = lins[0](x), lins[1](x)
+    want = TF.silu(yg) * yu
+    plain = fused(x).view(m, n, 2)                                 # the interleaved weight through the plain GEMV
+    if n >= 2400:                                                  # same k-split as the separate layers: bit-exact
+        assert torch.equal(plain[..., 0], yg) and torch.equal(plain[..., 1], yu)
+    got = D.linear_silu_pairs(fused, x)
+    assert got.shape == (m, n)
+    assert ((got.float() - want.float()).abs() <= 2.0 ** -6 * want.float().abs() + 1e-6).all()
+    assert (got == want).float().mean() > 0.97
+    # the fused epilogue IS the plain GEMV + tg_decode_silu_mul, bit for bit
+    for r in range(m):
+        assert torch.equal(got[r:r + 1], D.silu_mul(torch.cat([plain[r:r + 1, :, 0], plain[r:r + 1, :, 1]], -1).contiguous()))
