@@ -219,12 +219,272 @@ __global__ void __launch_bounds__(kThreads) gemm_frag_kernel(const GParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Streaming variant (int8 and 16-bit weights; the default).  Same decode arithmetic as above, restructured for
+// memory-level parallelism: a lane's words of one "unit" (IK consecutive k-tiles) are contiguous in every packed
+// layout, so they are fetched with 16-byte loads, U units (plus their scale/zero words) are in flight per lane
+// before anything is decoded, and the activations are staged once per CTA in shared memory (zero-padded to whole
+// units) instead of being re-read from global memory with bounds checks per k-tile.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxXSmem = 64 * 1024;
+
+template <int N>
+__device__ __forceinline__ void load_words(const uint32_t* __restrict__ src, uint32_t* dst) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+      dst[4 * i] = v.x, dst[4 * i + 1] = v.y, dst[4 * i + 2] = v.z, dst[4 * i + 3] = v.w;
+    }
+  } else if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(src) + i);
+      dst[2 * i] = v.x, dst[2 * i + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = __ldg(src + i);
+  }
+}
+
+// two int8 codes (bits 0..7 and 16..23 of `two`) -> (code - 128) * s + z for both, single-rounded in the activation
+// dtype like fma_dt(), returned as floats.  No int->float conversion instructions: bit patterns + one exact HSUB2.
+template <tg_dtype DT>
+__device__ __forceinline__ float2 decode8_pair(uint32_t two, uint32_t s2, uint32_t z2) {
+  if constexpr (DT == TG_FP16) {
+    const uint32_t h = (two & 0x00ff00ffu) | 0x64006400u;
+    const __half2 v = __hsub2(*reinterpret_cast<const __half2*>(&h), __floats2half2_rn(1152.f, 1152.f));
+    const __half2 w = __hfma2(v, *reinterpret_cast<const __half2*>(&s2), *reinterpret_cast<const __half2*>(&z2));
+    return __half22float2(w);
+  } else {
+    // bf16 has 8 significant bits: t = 128 + (b & 127) and the offset 256 - (b & 128) are both exact, and so is
+    // t - offset = b - 128
+    const uint32_t tt = (two & 0x007f007fu) | 0x43004300u;
+    const uint32_t off = 0x43804380u ^ (two & 0x00800080u);
+    const __nv_bfloat162 v = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&tt), *reinterpret_cast<const __nv_bfloat162*>(&off));
+    const __nv_bfloat162 w = __hfma2(v, *reinterpret_cast<const __nv_bfloat162*>(&s2),
+                                     *reinterpret_cast<const __nv_bfloat162*>(&z2));
+    const uint32_t wb = *reinterpret_cast<const uint32_t*>(&w);
+    return make_float2(__uint_as_float(wb << 16), __uint_as_float(wb & 0xffff0000u));
+  }
+}
+
+template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK, int MAXA>
+__global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const GParams p, int rows_per_pass, int kpad) {
+  static_assert(KIND != W4, "4-bit weights have their own kernels");
+  constexpr int NV = ALAYOUT ? 8 : 4;
+  constexpr int ROWS = ALAYOUT ? 16 : 8;
+  constexpr int RH = ALAYOUT ? 2 : 1;
+  constexpr int WPT = KIND == W8 ? (ALAYOUT ? 2 : 1) : (ALAYOUT ? 4 : 2);  // words per lane per k-tile
+  constexpr int NW = IK * WPT;                                               // ... per unit, contiguous
+  constexpr int U0 = (32 / NW) < (16 / (IK * RH)) ? (32 / NW) : (16 / (IK * RH));
+  constexpr int U = U0 < 1 ? 1 : (U0 > 8 ? 8 : U0);                          // units in flight per lane
+  extern __shared__ __align__(16) uint8_t xs_raw[];
+  uint16_t* xs = reinterpret_cast<uint16_t*>(xs_raw);                        // [rows_per_pass][kpad]
+  __shared__ float red[kWarps][MAXA][ROWS];   // MAXA: activation rows per pass this instantiation is unrolled for
+
+  const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+  const int g = t >> 2, q = t & 3;
+  const int n_units = p.outer_k;  // units per row tile
+  const int n_tiles = p.w_rows / ROWS;
+  const uint32_t* szw = reinterpret_cast<const uint32_t*>(p.sz);
+  const bool vec_ok = ((p.k & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+
+  uint32_t raw[U][NW];
+  uint32_t szv[U][IK][RH];
+  // one batch = U units of row tile rt, starting at unit u0 (stride kWarps): all loads are issued before any use
+  auto load_batch = [&](int rt, int u0) {
+    const uint32_t* wrow = p.w + ((int64_t)rt * n_units * 32 + t) * NW;
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int u = u0 + j * kWarps;
+      if (u < n_units) {
+        load_words<NW>(wrow + (int64_t)u * 32 * NW, raw[j]);
+        if constexpr (KIND == W8) {
+#pragma unroll
+          for (int ki = 0; ki < IK; ++ki) {
+            const int grp = min(((u * IK + ki) * 16) >> p.glog2, (p.k >> p.glog2) - 1);  // (padding tiles: any group)
+#pragma unroll
+            for (int h = 0; h < RH; ++h) szv[j][ki][h] = __ldg(szw + (int64_t)grp * p.w_rows + rt * ROWS + g + 8 * h);
+          }
+        }
+      }
+    }
+  };
+
+  for (int a0 = 0; a0 < p.rows_x; a0 += rows_per_pass) {
+    const int na = min(rows_per_pass, p.rows_x - a0);
+    int rt = blockIdx.x;
+    bool preloaded = false;
+    if (rt < n_tiles) {  // the first weight batch is in flight while the activations are staged
+      load_batch(rt, warp);
+      preloaded = true;
+    }
+    // stage the activations of this pass: 16-byte pieces, zero beyond k
+    for (int i = threadIdx.x; i < na * (kpad >> 3); i += kThreads) {
+      const int a = i / (kpad >> 3), c = (i % (kpad >> 3)) * 8;
+      const uint16_t* xr = p.x + (int64_t)(a0 + a) * p.k;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (c + 8 <= p.k && vec_ok) {
+        v = *reinterpret_cast<const uint4*>(xr + c);
+      } else {
+        uint16_t e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = (c + j < p.k) ? xr[c + j] : (uint16_t)0;
+        v = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+      }
+      *reinterpret_cast<uint4*>(xs + (size_t)a * kpad + c) = v;
+    }
+    __syncthreads();
+
+    for (; rt < n_tiles; rt += gridDim.x) {  // persistent over row tiles: the staged activations are reused
+      float acc[MAXA][RH];
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+#pragma unroll
+        for (int h = 0; h < RH; ++h) acc[a][h] = 0.f;
+
+      for (int u0 = warp; u0 < n_units; u0 += kWarps * U) {
+        if (!preloaded) load_batch(rt, u0);
+        preloaded = false;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int u = u0 + j * kWarps;
+          if (u >= n_units) break;
+#pragma unroll
+          for (int ki = 0; ki < IK; ++ki) {
+            float w[NV];
+            const uint32_t* rw = &raw[j][ki * WPT];
+            if constexpr (KIND == W16) {
+#pragma unroll
+              for (int i = 0; i < NV; ++i) w[i] = to_f32<DT>((uint16_t)(rw[i >> 1] >> (16 * (i & 1))));
+            } else {
+              // fragment value i sits in byte (i>>1) + 2*(i&1) of its word: pairs (0,1) / (2,3) are bytes (0,2) / (1,3)
+#pragma unroll
+              uint32_t s2[RH], z2[RH];
+#pragma unroll
+              for (int h = 0; h < RH; ++h) {
+                s2[h] = __byte_perm(szv[j][ki][h], 0, 0x1010);
+                z2[h] = __byte_perm(szv[j][ki][h], 0, 0x3232);
+              }
+#pragma unroll
+              for (int pr = 0; pr < NV / 2; ++pr) {
+                const uint32_t word = ALAYOUT ? rw[pr >> 1] : rw[0];
+                const float2 f = decode8_pair<DT>(word >> (8 * (pr & 1)), s2[ALAYOUT ? (pr & 1) : 0], z2[ALAYOUT ? (pr & 1) : 0]);
+                w[2 * pr] = f.x;
+                w[2 * pr + 1] = f.y;
+              }
+            }
+            const int kc = (u * IK + ki) * 16 + 2 * q;
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a) {
+              if (a < na) {
+                const uint32_t x01 = *reinterpret_cast<const uint32_t*>(xs + (size_t)a * kpad + kc);
+                const uint32_t x89 = *reinterpret_cast<const uint32_t*>(xs + (size_t)a * kpad + kc + 8);
+                const float xv[4] = {to_f32<DT>((uint16_t)x01), to_f32<DT>((uint16_t)(x01 >> 16)),
+                                     to_f32<DT>((uint16_t)x89), to_f32<DT>((uint16_t)(x89 >> 16))};
+                if constexpr (ALAYOUT) {
+                  acc[a][0] = fmaf(w[0], xv[0], acc[a][0]);
+                  acc[a][0] = fmaf(w[1], xv[1], acc[a][0]);
+                  acc[a][0] = fmaf(w[4], xv[2], acc[a][0]);
+                  acc[a][0] = fmaf(w[5], xv[3], acc[a][0]);
+                  acc[a][1] = fmaf(w[2], xv[0], acc[a][1]);
+                  acc[a][1] = fmaf(w[3], xv[1], acc[a][1]);
+                  acc[a][1] = fmaf(w[6], xv[2], acc[a][1]);
+                  acc[a][1] = fmaf(w[7], xv[3], acc[a][1]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) acc[a][0] = fmaf(w[i], xv[i], acc[a][0]);
+                }
+              }
+            }
+          }
+        }
+      }
+      // the next row tile's first batch is in flight during the reduction
+      if (rt + (int)gridDim.x < n_tiles) {
+        load_batch(rt + (int)gridDim.x, warp);
+        preloaded = true;
+      }
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+#pragma unroll
+        for (int h = 0; h < RH; ++h) {
+          float v = acc[a][h];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          if (q == 0) red[warp][a][g + 8 * h] = v;
+        }
+      __syncthreads();
+      for (int i = threadIdx.x; i < na * ROWS; i += kThreads) {
+        const int a = i / ROWS, r = i % ROWS;
+        float s = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < kWarps; ++w2) s += red[w2][a][r];
+        p.y[(int64_t)(a0 + a) * p.w_rows + rt * ROWS + r] = from_f32<DT>(s);
+      }
+      __syncthreads();
+    }
+    __syncthreads();  // everyone is done with the staged activations before the next pass overwrites them
+  }
+}
+
 template <tg_dtype DT, Kind KIND, bool ALAYOUT>
-int launch(const GParams& p, cudaStream_t st) {
+int launch_simple(const GParams& p, cudaStream_t st) {
   const int tiles = p.w_rows / (ALAYOUT ? 16 : 8);
   gemm_frag_kernel<DT, KIND, ALAYOUT><<<tiles, kThreads, 0, st>>>(p);
   TG_CHECK_LAUNCH("gemm_frag_kernel");
   return TG_OK;
+}
+
+template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK, int MAXA>
+int launch_stream_a(const GParams& p, int rows_per_pass, int kpad, cudaStream_t st) {
+  const size_t smem = (size_t)rows_per_pass * kpad * 2;
+  auto kern = gemm_stream_kernel<DT, KIND, ALAYOUT, IK, MAXA>;
+  static thread_local int ctas_per_sm = 0, n_sm = 0;
+  if (ctas_per_sm == 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxXSmem) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm_stream_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return TG_ERR_CUDA;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    int occ = 0;  // with a typical 8-16 KiB of staged activations
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 16 * 1024) != cudaSuccess || occ <= 0) occ = 2;
+    ctas_per_sm = occ;
+  }
+  const int tiles = p.w_rows / (ALAYOUT ? 16 : 8);
+  const int slots = ctas_per_sm * n_sm;  // persistent: the resident CTAs walk over the row tiles
+  const int grid = tiles < slots ? tiles : slots;
+  kern<<<grid, kThreads, smem, st>>>(p, rows_per_pass, kpad);
+  TG_CHECK_LAUNCH("gemm_stream_kernel");
+  return TG_OK;
+}
+
+template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK>
+int launch_stream(const GParams& p, cudaStream_t st) {
+  const int kpad = p.outer_k * IK * 16;
+  int rows_per_pass = kMaxXSmem / (kpad * 2);
+  if (rows_per_pass < 1) return launch_simple<DT, KIND, ALAYOUT>(p, st);  // very long k: activations stay in global memory
+  if (rows_per_pass > kActs) rows_per_pass = kActs;
+  if (rows_per_pass > p.rows_x) rows_per_pass = p.rows_x;
+  if (rows_per_pass == 1) return launch_stream_a<DT, KIND, ALAYOUT, IK, 1>(p, 1, kpad, st);
+  if (rows_per_pass <= 4) return launch_stream_a<DT, KIND, ALAYOUT, IK, 4>(p, rows_per_pass, kpad, st);
+  return launch_stream_a<DT, KIND, ALAYOUT, IK, 8>(p, rows_per_pass, kpad, st);
+}
+
+template <tg_dtype DT, Kind KIND, bool ALAYOUT>
+int launch(const GParams& p, cudaStream_t st) {
+  if (KIND == W16 && ALAYOUT) return launch_stream<DT, KIND, ALAYOUT, 1>(p, st);  // no inner k in this layout
+  switch (p.ik) {
+    case 1: return launch_stream<DT, KIND, ALAYOUT, 1>(p, st);
+    case 2: return launch_stream<DT, KIND, ALAYOUT, 2>(p, st);
+    case 4: return launch_stream<DT, KIND, ALAYOUT, 4>(p, st);
+    case 8: return launch_stream<DT, KIND, ALAYOUT, 8>(p, st);
+  }
+  return launch_simple<DT, KIND, ALAYOUT>(p, st);
 }
 
 template <Kind KIND>

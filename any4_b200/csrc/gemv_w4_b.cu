@@ -391,7 +391,9 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
     const uint32_t w_lane_off = tile_off(rlane >> 3) + (uint32_t)warp * kTileChunkBytes +
                                 (uint32_t)(rlane & 7) * Geo<IK>::kRowStride;
     uint32_t xr0[4] = {0u, 0u, 0u, 0u}, xr1[4] = {0u, 0u, 0u, 0u};  // x fragments (stay zero on inactive lanes)
-    uint32_t xs0[4] = {0u, 0u, 0u, 0u}, xs1[4] = {0u, 0u, 0u, 0u};  // rows mi+2 (!M1)
+    // !M1: one set of operand registers for all words (rows mi: xa/xb, rows mi+2: xc/xd; second tile: ya..yd); they are
+    // only ever written by predicated loads, so the inactive lanes keep the zeros the block structure needs
+    uint32_t xa_ = 0u, xb_ = 0u, xc_ = 0u, xd_ = 0u, ya_ = 0u, yb_ = 0u, yc_ = 0u, yd_ = 0u;
     constexpr int kChains = 2;            // independent HMMA accumulation chains
     const int nj = M1 ? 1 : p.m;
     const int tj = threadIdx.x >> 5, trow = threadIdx.x & 31;  // epilogue thread (tj, trow) owns y[tj][row0 + trow]
@@ -490,14 +492,13 @@ __device__ __forceinline__ void gemv_w4_b_body(const Params& p, const Peers& pee
                 // A = weights: a0/a2 = k-set 1 (tile 2tp), a1/a3 = k-set 2 (tile 2tp+1)
                 mma16816<DT>(acc[i & 1], p0, p1, p2, p3, xr0[i], xr1[i]);
               } else {
-                lds64_if(xr0[i], xr1[i], xo, xa01);
-                lds64_if(xs0[i], xs1[i], xo + x_row2, xa23);
+                lds64_if(xa_, xb_, xo, xa01);
+                lds64_if(xc_, xd_, xo + x_row2, xa23);
+                lds64_if(ya_, yb_, xo + 32u, xa01);
+                lds64_if(yc_, yd_, xo + 32u + x_row2, xa23);
                 // tile 2tp: B = (byte0, byte2); A = x (a0,a2 rows mi, a1,a3 rows mi+2)
-                mma16816<DT>(acc[i & 1], xr0[i], xs0[i], xr1[i], xs1[i], p0, p2);
-                uint32_t y0 = 0u, y1 = 0u, v0 = 0u, v1 = 0u;
-                lds64_if(y0, y1, xo + 32u, xa01);
-                lds64_if(v0, v1, xo + 32u + x_row2, xa23);
-                mma16816<DT>(acc[i & 1], y0, v0, y1, v1, p1, p3);
+                mma16816<DT>(acc[i & 1], xa_, xc_, xb_, xd_, p0, p2);
+                mma16816<DT>(acc[i & 1], ya_, yc_, yb_, yd_, p1, p3);
               }
             }
           }
