@@ -1,19 +1,18 @@
-// Fragment-order weight-only GEMM for every packed format that is NOT the tuned B-layout
-// 4-bit kernel (gemv_w4_b.cu): int4/any4/mx4 in the "A" layout (weight on the left), int8 and
-// 16-bit weights in either layout.
+// Weight-only GEMM for int8 and 16-bit packed weights, in either layout (4-bit weights have their own kernels:
+// gemv_w4_b.cu, gemv_w4_a.cu).
 //
-// Replaces tinygemm_m16n8k16_chunk_kernel instantiated with ALayout_TC_int4 / *_int8 / *_TC
-// (reference: TinyGemmImpl.cuh:23-345, MatrixLayoutA.cuh:375-1062, MatrixLayoutB.cuh:461-684,
+// Replaces tinygemm_m16n8k16_chunk_kernel instantiated with *Layout_TC_int8 / *Layout_TC
+// (reference: TinyGemmImpl.cuh:23-345, MatrixLayoutA.cuh:211-373, :818-1062, MatrixLayoutB.cuh:461-684,
 // :1103-1328, Dequantization.cuh:265-328).
 //
-// One CTA owns one weight row tile (16 rows in the A layout, 8 in the B layout); its warps
-// split the k-tiles.  A lane reads exactly the words the packed layout assigns to its lane
-// id, so every warp load is one fully coalesced 128..512-byte run, decodes them to the
-// activation dtype with the reference's single-rounded FMA, and accumulates exact products in
-// fp32 (FFMA on up-converted operands: a bf16/fp16 product is exact in fp32, so this is the
-// same arithmetic as the tensor core's fp32 accumulate).  The four lanes that share a weight
-// row are combined with warp shuffles, the warps through shared memory, one RN at the end.
+// gemm_stream_kernel (default): the packed layouts are mma.m16n8k16 fragment orders, and the words a lane owns for IK
+// consecutive k-tiles are contiguous.  A CTA (8 warps splitting k) walks over row tiles (persistent grid), stages the
+// activations once in shared memory, fetches U units per lane with 16-byte loads before decoding any of them, decodes
+// int8 with bit patterns + one exact HSUB2 + the reference's single-rounded FMA, and feeds the words straight into
+// mma.sync (fp32 accumulation of exact products).  Warps are combined through shared memory, one RN at the end.
+// gemm_frag_kernel: the simple per-k-tile FFMA version, kept for k too long to stage the activations.
 #include "common.cuh"
+#include "w4_common.cuh"  // mma16816
 
 namespace tg {
 namespace {
@@ -249,14 +248,14 @@ __device__ __forceinline__ void load_words(const uint32_t* __restrict__ src, uin
 }
 
 // two int8 codes (bits 0..7 and 16..23 of `two`) -> (code - 128) * s + z for both, single-rounded in the activation
-// dtype like fma_dt(), returned as floats.  No int->float conversion instructions: bit patterns + one exact HSUB2.
+// dtype like fma_dt(), as a packed pair.  No int->float conversion instructions: bit patterns + one exact HSUB2.
 template <tg_dtype DT>
-__device__ __forceinline__ float2 decode8_pair(uint32_t two, uint32_t s2, uint32_t z2) {
+__device__ __forceinline__ uint32_t decode8_pair(uint32_t two, uint32_t s2, uint32_t z2) {
   if constexpr (DT == TG_FP16) {
-    const uint32_t h = (two & 0x00ff00ffu) | 0x64006400u;
+    const uint32_t h = (two & 0x00ff00ffu) | 0x64006400u;  // 1024 + b
     const __half2 v = __hsub2(*reinterpret_cast<const __half2*>(&h), __floats2half2_rn(1152.f, 1152.f));
     const __half2 w = __hfma2(v, *reinterpret_cast<const __half2*>(&s2), *reinterpret_cast<const __half2*>(&z2));
-    return __half22float2(w);
+    return *reinterpret_cast<const uint32_t*>(&w);
   } else {
     // bf16 has 8 significant bits: t = 128 + (b & 127) and the offset 256 - (b & 128) are both exact, and so is
     // t - offset = b - 128
@@ -265,24 +264,28 @@ __device__ __forceinline__ float2 decode8_pair(uint32_t two, uint32_t s2, uint32
     const __nv_bfloat162 v = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&tt), *reinterpret_cast<const __nv_bfloat162*>(&off));
     const __nv_bfloat162 w = __hfma2(v, *reinterpret_cast<const __nv_bfloat162*>(&s2),
                                      *reinterpret_cast<const __nv_bfloat162*>(&z2));
-    const uint32_t wb = *reinterpret_cast<const uint32_t*>(&w);
-    return make_float2(__uint_as_float(wb << 16), __uint_as_float(wb & 0xffff0000u));
+    return *reinterpret_cast<const uint32_t*>(&w);
   }
 }
 
-template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK, int MAXA>
+// The packed layouts ARE mma.m16n8k16 fragment orders, so the decoded words go straight into the tensor core:
+//   A layout (weight on the left):  A operand = 16 weight rows x 16 k, B operand = activations (k x 8 rows)
+//   B layout (weight on the right): B operand = 16 k x 8 weight rows,  A operand = activations (16 rows x k)
+// fp32 accumulation of exact products, as in the reference.  HI: activation rows 8..15 of a pass exist (B layout).
+template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK, bool HI>
 __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const GParams p, int rows_per_pass, int kpad) {
   static_assert(KIND != W4, "4-bit weights have their own kernels");
-  constexpr int NV = ALAYOUT ? 8 : 4;
+  static_assert(!(ALAYOUT && HI), "the A layout carries at most 8 activation rows per mma");
   constexpr int ROWS = ALAYOUT ? 16 : 8;
   constexpr int RH = ALAYOUT ? 2 : 1;
-  constexpr int WPT = KIND == W8 ? (ALAYOUT ? 2 : 1) : (ALAYOUT ? 4 : 2);  // words per lane per k-tile
+  constexpr int NP = ALAYOUT ? 4 : 2;                                        // packed value pairs per lane per k-tile
+  constexpr int WPT = KIND == W8 ? (ALAYOUT ? 2 : 1) : NP;                   // words per lane per k-tile
   constexpr int NW = IK * WPT;                                               // ... per unit, contiguous
   constexpr int U0 = (32 / NW) < (16 / (IK * RH)) ? (32 / NW) : (16 / (IK * RH));
   constexpr int U = U0 < 1 ? 1 : (U0 > 8 ? 8 : U0);                          // units in flight per lane
   extern __shared__ __align__(16) uint8_t xs_raw[];
   uint16_t* xs = reinterpret_cast<uint16_t*>(xs_raw);                        // [rows_per_pass][kpad]
-  __shared__ float red[kWarps][MAXA][ROWS];   // MAXA: activation rows per pass this instantiation is unrolled for
+  __shared__ float red[kWarps][4][32];
 
   const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
   const int g = t >> 2, q = t & 3;
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const GParams p, 
   const int n_tiles = p.w_rows / ROWS;
   const uint32_t* szw = reinterpret_cast<const uint32_t*>(p.sz);
   const bool vec_ok = ((p.k & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+  const bool one_group_per_unit = (1 << p.glog2) >= IK * 16;
 
   uint32_t raw[U][NW];
   uint32_t szv[U][IK][RH];
@@ -302,11 +306,22 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const GParams p, 
       if (u < n_units) {
         load_words<NW>(wrow + (int64_t)u * 32 * NW, raw[j]);
         if constexpr (KIND == W8) {
+          const int n_groups = p.k >> p.glog2;
+          if (one_group_per_unit) {
+            const int grp = min((u * IK * 16) >> p.glog2, n_groups - 1);  // (padding tiles: any group)
 #pragma unroll
-          for (int ki = 0; ki < IK; ++ki) {
-            const int grp = min(((u * IK + ki) * 16) >> p.glog2, (p.k >> p.glog2) - 1);  // (padding tiles: any group)
+            for (int h = 0; h < RH; ++h) {
+              const uint32_t v = __ldg(szw + (int64_t)grp * p.w_rows + rt * ROWS + g + 8 * h);
 #pragma unroll
-            for (int h = 0; h < RH; ++h) szv[j][ki][h] = __ldg(szw + (int64_t)grp * p.w_rows + rt * ROWS + g + 8 * h);
+              for (int ki = 0; ki < IK; ++ki) szv[j][ki][h] = v;
+            }
+          } else {
+#pragma unroll
+            for (int ki = 0; ki < IK; ++ki) {
+              const int grp = min(((u * IK + ki) * 16) >> p.glog2, n_groups - 1);
+#pragma unroll
+              for (int h = 0; h < RH; ++h) szv[j][ki][h] = __ldg(szw + (int64_t)grp * p.w_rows + rt * ROWS + g + 8 * h);
+            }
           }
         }
       }
@@ -337,13 +352,17 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const GParams p, 
       *reinterpret_cast<uint4*>(xs + (size_t)a * kpad + c) = v;
     }
     __syncthreads();
+    // this lane's activation rows (g and, with HI, g + 8); rows beyond the pass contribute zeros
+    const bool has_lo = g < na, has_hi = HI && (g + 8 < na);
+    const uint16_t* x_lo = xs + (size_t)(has_lo ? g : 0) * kpad + 2 * q;
+    const uint16_t* x_hi = xs + (size_t)(has_hi ? g + 8 : 0) * kpad + 2 * q;
 
     for (; rt < n_tiles; rt += gridDim.x) {  // persistent over row tiles: the staged activations are reused
-      float acc[MAXA][RH];
+      float acc[2][4];
 #pragma unroll
-      for (int a = 0; a < MAXA; ++a)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int h = 0; h < RH; ++h) acc[a][h] = 0.f;
+        for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
 
       for (int u0 = warp; u0 < n_units; u0 += kWarps * U) {
         if (!preloaded) load_batch(rt, u0);
@@ -354,14 +373,13 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const GParams p, 
           if (u >= n_units) break;
 #pragma unroll
           for (int ki = 0; ki < IK; ++ki) {
-            float w[NV];
+            uint32_t wv[NP];
             const uint32_t* rw = &raw[j][ki * WPT];
             if constexpr (KIND == W16) {
 #pragma unroll
-              for (int i = 0; i < NV; ++i) w[i] = to_f32<DT>((uint16_t)(rw[i >> 1] >> (16 * (i & 1))));
+              for (int i = 0; i < NP; ++i) wv[i] = rw[i];
             } else {
               // fragment value i sits in byte (i>>1) + 2*(i&1) of its word: pairs (0,1) / (2,3) are bytes (0,2) / (1,3)
-#pragma unroll
               uint32_t s2[RH], z2[RH];
 #pragma unroll
               for (int h = 0; h < RH; ++h) {
@@ -369,35 +387,24 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const GParams p, 
                 z2[h] = __byte_perm(szv[j][ki][h], 0, 0x3232);
               }
 #pragma unroll
-              for (int pr = 0; pr < NV / 2; ++pr) {
+              for (int pr = 0; pr < NP; ++pr) {
                 const uint32_t word = ALAYOUT ? rw[pr >> 1] : rw[0];
-                const float2 f = decode8_pair<DT>(word >> (8 * (pr & 1)), s2[ALAYOUT ? (pr & 1) : 0], z2[ALAYOUT ? (pr & 1) : 0]);
-                w[2 * pr] = f.x;
-                w[2 * pr + 1] = f.y;
+                wv[pr] = decode8_pair<DT>(word >> (8 * (pr & 1)), s2[ALAYOUT ? (pr & 1) : 0], z2[ALAYOUT ? (pr & 1) : 0]);
               }
             }
-            const int kc = (u * IK + ki) * 16 + 2 * q;
-#pragma unroll
-            for (int a = 0; a < MAXA; ++a) {
-              if (a < na) {
-                const uint32_t x01 = *reinterpret_cast<const uint32_t*>(xs + (size_t)a * kpad + kc);
-                const uint32_t x89 = *reinterpret_cast<const uint32_t*>(xs + (size_t)a * kpad + kc + 8);
-                const float xv[4] = {to_f32<DT>((uint16_t)x01), to_f32<DT>((uint16_t)(x01 >> 16)),
-                                     to_f32<DT>((uint16_t)x89), to_f32<DT>((uint16_t)(x89 >> 16))};
-                if constexpr (ALAYOUT) {
-                  acc[a][0] = fmaf(w[0], xv[0], acc[a][0]);
-                  acc[a][0] = fmaf(w[1], xv[1], acc[a][0]);
-                  acc[a][0] = fmaf(w[4], xv[2], acc[a][0]);
-                  acc[a][0] = fmaf(w[5], xv[3], acc[a][0]);
-                  acc[a][1] = fmaf(w[2], xv[0], acc[a][1]);
-                  acc[a][1] = fmaf(w[3], xv[1], acc[a][1]);
-                  acc[a][1] = fmaf(w[6], xv[2], acc[a][1]);
-                  acc[a][1] = fmaf(w[7], xv[3], acc[a][1]);
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) acc[a][0] = fmaf(w[i], xv[i], acc[a][0]);
-                }
+            const int kt = (u * IK + ki) * 16;
+            const uint32_t xl0 = has_lo ? *reinterpret_cast<const uint32_t*>(x_lo + kt) : 0u;
+            const uint32_t xl1 = has_lo ? *reinterpret_cast<const uint32_t*>(x_lo + kt + 8) : 0u;
+            if constexpr (ALAYOUT) {
+              // pairs: (g,k0..1) (g+8,k0..1) (g,k0+8..9) (g+8,k0+8..9) = a0..a3
+              w4::mma16816<DT>(acc[(ki + j) & 1], wv[0], wv[1], wv[2], wv[3], xl0, xl1);
+            } else {
+              uint32_t xh0 = 0u, xh1 = 0u;
+              if constexpr (HI) {
+                xh0 = has_hi ? *reinterpret_cast<const uint32_t*>(x_hi + kt) : 0u;
+                xh1 = has_hi ? *reinterpret_cast<const uint32_t*>(x_hi + kt + 8) : 0u;
               }
+              w4::mma16816<DT>(acc[(ki + j) & 1], xl0, xh0, xl1, xh1, wv[0], wv[1]);
             }
           }
         }
@@ -408,21 +415,17 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const GParams p, 
         preloaded = true;
       }
 #pragma unroll
-      for (int a = 0; a < MAXA; ++a)
-#pragma unroll
-        for (int h = 0; h < RH; ++h) {
-          float v = acc[a][h];
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          if (q == 0) red[warp][a][g + 8 * h] = v;
-        }
+      for (int i = 0; i < 4; ++i) red[warp][i][t] = acc[0][i] + acc[1][i];
       __syncthreads();
-      for (int i = threadIdx.x; i < na * ROWS; i += kThreads) {
-        const int a = i / ROWS, r = i % ROWS;
-        float s = 0.f;
+      if (threadIdx.x < 128) {
+        const int ci = threadIdx.x >> 5, gl = (threadIdx.x & 31) >> 2, ql = threadIdx.x & 3;
+        float sum = 0.f;
 #pragma unroll
-        for (int w2 = 0; w2 < kWarps; ++w2) s += red[w2][a][r];
-        p.y[(int64_t)(a0 + a) * p.w_rows + rt * ROWS + r] = from_f32<DT>(s);
+        for (int w2 = 0; w2 < kWarps; ++w2) sum += red[w2][ci][threadIdx.x & 31];
+        // C fragment: c0,c1 = (row g, cols 2q, 2q+1), c2,c3 = (row g+8, ...)
+        const int crow = gl + 8 * (ci >> 1), ccol = 2 * ql + (ci & 1);
+        const int act = ALAYOUT ? ccol : crow, wrow = ALAYOUT ? crow : ccol;
+        if (act < na) p.y[(int64_t)(a0 + act) * p.w_rows + rt * ROWS + wrow] = from_f32<DT>(sum);
       }
       __syncthreads();
     }
@@ -438,10 +441,10 @@ int launch_simple(const GParams& p, cudaStream_t st) {
   return TG_OK;
 }
 
-template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK, int MAXA>
+template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK, bool HI>
 int launch_stream_a(const GParams& p, int rows_per_pass, int kpad, cudaStream_t st) {
   const size_t smem = (size_t)rows_per_pass * kpad * 2;
-  auto kern = gemm_stream_kernel<DT, KIND, ALAYOUT, IK, MAXA>;
+  auto kern = gemm_stream_kernel<DT, KIND, ALAYOUT, IK, HI>;
   static thread_local int ctas_per_sm = 0, n_sm = 0;
   if (ctas_per_sm == 0) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxXSmem) != cudaSuccess) {
@@ -468,11 +471,13 @@ int launch_stream(const GParams& p, cudaStream_t st) {
   const int kpad = p.outer_k * IK * 16;
   int rows_per_pass = kMaxXSmem / (kpad * 2);
   if (rows_per_pass < 1) return launch_simple<DT, KIND, ALAYOUT>(p, st);  // very long k: activations stay in global memory
-  if (rows_per_pass > kActs) rows_per_pass = kActs;
+  const int cap = ALAYOUT ? 8 : 16;  // activation rows one mma carries
+  if (rows_per_pass > cap) rows_per_pass = cap;
   if (rows_per_pass > p.rows_x) rows_per_pass = p.rows_x;
-  if (rows_per_pass == 1) return launch_stream_a<DT, KIND, ALAYOUT, IK, 1>(p, 1, kpad, st);
-  if (rows_per_pass <= 4) return launch_stream_a<DT, KIND, ALAYOUT, IK, 4>(p, rows_per_pass, kpad, st);
-  return launch_stream_a<DT, KIND, ALAYOUT, IK, 8>(p, rows_per_pass, kpad, st);
+  if constexpr (!ALAYOUT) {
+    if (rows_per_pass > 8) return launch_stream_a<DT, KIND, ALAYOUT, IK, true>(p, rows_per_pass, kpad, st);
+  }
+  return launch_stream_a<DT, KIND, ALAYOUT, IK, false>(p, rows_per_pass, kpad, st);
 }
 
 template <tg_dtype DT, Kind KIND, bool ALAYOUT>
