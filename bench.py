@@ -50,6 +50,23 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the headline kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    `ncu --set full` capture of this same kernel and shape (profiles/r1/ncu_prof_summary.txt); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r1", "ncu_prof_summary.txt")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        tot = 0.0
+        for line in open(path):
+            f = line.rstrip("\n").split("\t")
+            if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                vals = [float(v) for v in f[2:] if v]
+                tot += scale[f[1]] * sum(vals) / len(vals)
+        return tot or None
+    except Exception:
+        return None
+
+
 def synth_layer(n, k, seed, device, rows=None):
     """Synthetic any4 layer (SURVEY.md 8d recipe), generated on the device: packed codes are
     uniformly random nibbles, so the packed words are drawn directly (equivalent to packing
@@ -373,7 +390,7 @@ def run_ours(args):
                                                          "frac_of_peak": round(e["gbps"] / world / peak, 4)} for e in extra},
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src + " (of measured)",
+                         "traffic": ncu_traffic() if world == 1 else None, "peak_source": peak_src + " (of measured)",
                          "kernel": "gemv_w4_b_kernel<bf16, ik=4, m=1>", "us_per_launch": us,
                          "algorithmic_bytes_per_launch": per_rank_bytes},
             "e2e": {"value": head["e2e_gbps"], "unit": "GB/s", "h2d_bytes_per_step": head["h2d"],
