@@ -16,8 +16,11 @@
 //  * Group scale/zero are applied with one fma.rn.{bf16,f16}x2 per pair - the same single
 //    rounded FMA as the reference (MatrixLayoutB.cuh:1042-1046), so every dequantised weight
 //    is bit-identical to the reference's.
-//  * Weights stream HBM -> shared memory with 1-D bulk TMA (cp.async.bulk + mbarrier
-//    complete_tx) into warp-private multi-stage rings: no CTA-wide barrier in the k loop.
+//  * Weights stream HBM -> shared memory with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx, 4 KiB copies)
+//    into a CTA-wide ring of 3 x 32 KiB stages fed by a dedicated producer warp; a stage = 128 k per consumer
+//    warp, one full barrier per k half, one empty barrier per stage.  The CTA is persistent over row blocks.
+//  * Lane L owns row L with bits 2 and 3 swapped and the odd tile of a tile pair is staged a few bytes further,
+//    which makes the 16-byte weight loads bank-conflict free (row_of_lane / tile_off_t below).
 //  * The dot products go to the tensor pipe (mma.sync m16n8k16, fp32 accumulate) even at m = 1
 //    so the FMA pipe stays free for the dequant.  Because all 32 lanes hold DIFFERENT weight
 //    rows, the activation operand is block-structured: x sits in k-slots {2q,2q+1,2q+8,2q+9}
@@ -26,11 +29,16 @@
 //    same rows (256 useful MACs per HMMA); for m > 1 the weights are the B fragment and four
 //    activation rows ride in one HMMA.
 //  * Split-k for small n uses a thread-block cluster and a DSMEM reduction (no workspace).
+//  * Programmatic dependent launch: launch_dependents at entry, wait before the activations are read (before
+//    anything is read unless the caller declared the weights static).
+//  * Epilogue variants: plain store, store into every rank's symmetric buffer (row-sharded multi-GPU), and
+//    silu(gate) * up over row-interleaved gate/up weights.
 //
 // Numerics: dequantised weights bit-identical to the reference; products exact; fp32
 // accumulation (order differs from the reference, as allowed by SURVEY.md 3.6); one RN at
-// the end.  Non-finite weights (mx4 exponent 255) additionally poison the up to three other
-// rows that share an mma row with them (0 * NaN); the reference confines the NaN to its row.
+// the end.  Non-finite weights (mx4 exponent >= 254, Inf/NaN LUT or scale) would poison the up to three other
+// rows that share an mma row with them (0 * NaN); every CTA checks its sums and recomputes its rows one by one
+// (slow_rows) when one is non-finite, which confines the NaN to its row as the reference does.
 #include <cooperative_groups.h>
 
 #include <cstdlib>

@@ -35,8 +35,6 @@ constexpr uint32_t kDynSmemBytes = kCtrlBytes + kStageBytes + kTableBytes + kSta
 static_assert(kDynSmemBytes <= 232448u, "exceeds the 227 KiB opt-in shared memory of sm_100");
 constexpr int kMaxXBytes = 32768;      // capacity of the activation area (odd half-lines of the table)
 constexpr int kPreSz = 4;              // group words per thread prefetched into registers for the next row block
-constexpr int kPre = 8;                // x items per thread whose loads are issued before the TMA starts
-                                       // (8 x 512 threads covers all of one activation row and all staged group words)
 
 struct Params {
   const uint8_t* w;      // packed weight
