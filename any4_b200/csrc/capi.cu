@@ -19,6 +19,13 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches += (uint64_t)n; }
 
 void set_w4_options(int pdl, int static_weights);
+int launch_gemm_w4_frag_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut, const uint8_t* exps,
+                          int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik, tg_w4_format fmt, tg_dtype dt,
+                          const uint16_t* const_lut, cudaStream_t st);
+// activation rows from which the B-layout 4-bit GEMM uses the fragment-order kernel (gemv_w4_frag.cu); 0 = never.
+// Measured at 4096^2 (profiles/r1/frag_kernel_m_sweep.txt): one 8-row pass of it costs ~15.7 us, a 4-row pass of the
+// lane-per-row kernel ~8.7 us, so it wins from 13 rows on (2 passes vs 4).  tg_set_option(TG_OPT_FRAG_MIN_ROWS, v).
+int g_frag_min_rows = 13;
 int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
                         const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
                         tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st,
@@ -31,7 +38,7 @@ namespace {
 
 // int4 and mx4 run through the LUT kernels with a constant table per dtype
 // (reference: Dequantization.cuh:136-260 "code - 8", FloatDefs.cuh:18-34 kMX4_Values)
-__device__ uint16_t g_const_luts[4][16];  // [int4 bf16, int4 fp16, mx4 bf16, mx4 fp16]
+__device__ __align__(16) uint16_t g_const_luts[4][16];  // [int4 bf16, int4 fp16, mx4 bf16, mx4 fp16]
 
 __global__ void init_const_luts_kernel() {
   const int i = threadIdx.x;
@@ -110,6 +117,10 @@ int tg_set_option(tg_option option, int value) {
   switch (option) {
     case TG_OPT_PDL: set_w4_options(value != 0, -1); return TG_OK;
     case TG_OPT_STATIC_WEIGHTS: set_w4_options(-1, value != 0); return TG_OK;
+    case TG_OPT_FRAG_MIN_ROWS:
+      if (value < 0) break;
+      g_frag_min_rows = value;
+      return TG_OK;
   }
   set_error("tg_set_option: unknown option %d", (int)option);
   return TG_ERR_INVALID_ARGUMENT;
@@ -150,6 +161,12 @@ int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_z
     if (rc != TG_OK) return rc;
   }
   if (side == TG_WEIGHT_B) {
+    // more activation rows than the decode kernel carries per pass: fragment-order tensor-core kernel (gemv_w4_frag.cu)
+    if (g_frag_min_rows > 0 && rows_x >= g_frag_min_rows) {
+      rc = launch_gemm_w4_frag_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
+                                 (cudaStream_t)stream);
+      if (rc != -1) return rc;  // -1: shape not handled there (k too long to stage the activations)
+    }
     return launch_gemm_w4_rm_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
                                (cudaStream_t)stream);
   }

@@ -284,7 +284,10 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const GParams p, 
   constexpr int U0 = (32 / NW) < (16 / (IK * RH)) ? (32 / NW) : (16 / (IK * RH));
   constexpr int U = U0 < 1 ? 1 : (U0 > 8 ? 8 : U0);                          // units in flight per lane
   extern __shared__ __align__(16) uint8_t xs_raw[];
-  uint16_t* xs = reinterpret_cast<uint16_t*>(xs_raw);                        // [rows_per_pass][kpad]
+  uint16_t* xs = reinterpret_cast<uint16_t*>(xs_raw);                        // [rows_per_pass][xstride]
+  // row stride = kpad + 8 elements = 4 * odd words: the 8 activation rows x 4 k-pairs one operand load touches fall
+  // into 32 distinct banks (a stride of kpad alone would put all 8 rows into the same 4 banks)
+  const int xstride = kpad + 8;
   __shared__ float red[kWarps][4][32];
 
   const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
@@ -349,13 +352,13 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const GParams p, 
         for (int j = 0; j < 8; ++j) e[j] = (c + j < p.k) ? xr[c + j] : (uint16_t)0;
         v = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
       }
-      *reinterpret_cast<uint4*>(xs + (size_t)a * kpad + c) = v;
+      *reinterpret_cast<uint4*>(xs + (size_t)a * xstride + c) = v;
     }
     __syncthreads();
     // this lane's activation rows (g and, with HI, g + 8); rows beyond the pass contribute zeros
     const bool has_lo = g < na, has_hi = HI && (g + 8 < na);
-    const uint16_t* x_lo = xs + (size_t)(has_lo ? g : 0) * kpad + 2 * q;
-    const uint16_t* x_hi = xs + (size_t)(has_hi ? g + 8 : 0) * kpad + 2 * q;
+    const uint16_t* x_lo = xs + (size_t)(has_lo ? g : 0) * xstride + 2 * q;
+    const uint16_t* x_hi = xs + (size_t)(has_hi ? g + 8 : 0) * xstride + 2 * q;
 
     for (; rt < n_tiles; rt += gridDim.x) {  // persistent over row tiles: the staged activations are reused
       float acc[2][4];
@@ -443,7 +446,7 @@ int launch_simple(const GParams& p, cudaStream_t st) {
 
 template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK, bool HI>
 int launch_stream_a(const GParams& p, int rows_per_pass, int kpad, cudaStream_t st) {
-  const size_t smem = (size_t)rows_per_pass * kpad * 2;
+  const size_t smem = (size_t)rows_per_pass * (kpad + 8) * 2;
   auto kern = gemm_stream_kernel<DT, KIND, ALAYOUT, IK, HI>;
   static thread_local int ctas_per_sm = 0, n_sm = 0;
   if (ctas_per_sm == 0) {
@@ -469,7 +472,7 @@ int launch_stream_a(const GParams& p, int rows_per_pass, int kpad, cudaStream_t 
 template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK>
 int launch_stream(const GParams& p, cudaStream_t st) {
   const int kpad = p.outer_k * IK * 16;
-  int rows_per_pass = kMaxXSmem / (kpad * 2);
+  int rows_per_pass = kMaxXSmem / ((kpad + 8) * 2);
   if (rows_per_pass < 1) return launch_simple<DT, KIND, ALAYOUT>(p, st);  // very long k: activations stay in global memory
   const int cap = ALAYOUT ? 8 : 16;  // activation rows one mma carries
   if (rows_per_pass > cap) rows_per_pass = cap;

@@ -173,3 +173,42 @@ def test_large_shape_linearity_and_rows(cuda_device):
     assert _tol.frob_rel(y4[:1].cpu(), y1.cpu()) <= _tol.FROB_REL
     y0 = ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(torch.zeros_like(x_d[:1]), w2, g, sz_d, lut_d, True)
     assert (y0 == 0).all()
+
+
+@pytest.mark.parametrize("fmt", ["any4r", "int4", "mx4"])
+@pytest.mark.parametrize("m", [3, 8, 16])
+def test_fragment_kernel_agrees_with_decode_kernel(fmt, m):
+    """B-layout 4-bit GEMM: the fragment-order kernel (TG_OPT_FRAG_MIN_ROWS, default from 13 rows) and the
+    lane-per-row kernel dequantise identically and differ only in the order of the fp32 partial sums."""
+    import tinygemm  # noqa: F401
+    from any4_b200 import _native
+    from any4_b200 import utils as U
+
+    ops, lib = torch.ops.tinygemm, _native.capi()
+    dev = torch.device("cuda:0")
+    n, k, g = 264, 1024, 128
+    gen = torch.Generator(device=dev).manual_seed(m + len(fmt))
+    x = torch.randn(m, k, device=dev, generator=gen).bfloat16()
+    wf = torch.randn(n, k, device=dev, generator=gen).bfloat16()
+    if fmt == "mx4":
+        codes, exps = U.quantize_mx4(wf, 32)
+        w = ops.convert_matrix_to_m16n8k16_Bint4_layout(codes.to(torch.int32), 4)
+        run = lambda: ops.tinygemm_y_f16RM_x_f16RM_w_mx4TC(x, w, 32, exps, True)
+    else:
+        codes, sz = U.group_quantize_tensor(wf, 4, g)
+        w = ops.convert_matrix_to_m16n8k16_Bint4_layout(codes, 4)
+        if fmt == "int4":
+            run = lambda: ops.tinygemm_y_f16RM_x_f16RM_w_int4TC(x, w, g, sz, True)
+        else:
+            lut = (torch.rand(n, 16, device=dev, generator=gen) * 15).sort(1).values.bfloat16() - 8
+            run = lambda: ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(x, w, g, sz, lut, True)
+    try:
+        assert lib.tg_set_option(2, 0) == 0          # never the fragment kernel
+        ref = run()
+        assert lib.tg_set_option(2, 1) == 0          # always
+        got = run()
+    finally:
+        lib.tg_set_option(2, 13)
+    assert got.shape == ref.shape
+    assert ((got.float() - ref.float()).abs() <= 2.0 ** -7 * ref.float().abs() + 1e-3).all()
+    assert (got == ref).float().mean() > 0.9
