@@ -37,6 +37,15 @@ void count_launch(int n = 1);
 
 static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Function attributes (opt-in shared memory size) and occupancy are per DEVICE: one-time setup flags are kept per
+// thread and per device ordinal, so a process that drives several GPUs (CUDAGuard in the torch op layer) works too.
+constexpr int kMaxDevices = 64;
+static inline int current_device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+  return d % kMaxDevices;
+}
+
 // ---- internal launchers shared between translation units ---------------------------
 // (all return TG_OK / TG_ERR_*)
 int launch_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,

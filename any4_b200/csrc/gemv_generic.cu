@@ -448,7 +448,8 @@ template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK, bool HI>
 int launch_stream_a(const GParams& p, int rows_per_pass, int kpad, cudaStream_t st) {
   const size_t smem = (size_t)rows_per_pass * (kpad + 8) * 2;
   auto kern = gemm_stream_kernel<DT, KIND, ALAYOUT, IK, HI>;
-  static thread_local int ctas_per_sm = 0, n_sm = 0;
+  static thread_local int ctas_per_sm_dev[kMaxDevices] = {}, n_sm = 0;
+  int& ctas_per_sm = ctas_per_sm_dev[current_device_slot()];
   if (ctas_per_sm == 0) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxXSmem) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_stream_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -415,7 +415,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemv_w4_a_kernel(const Params p) 
 template <tg_dtype DT, int IK>
 int launch_a(const Params& p0, int row_blocks, int64_t rows_x, const uint16_t* x, uint16_t* y, cudaStream_t st) {
   auto kern = gemv_w4_a_kernel<DT, IK>;
-  static thread_local bool attr_set = false;
+  static thread_local bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBytes) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(smem=%u) failed: %s", kDynSmemBytes, cudaGetErrorString(cudaGetLastError()));

@@ -657,7 +657,8 @@ template <tg_dtype DT, int IK, bool M1>
 int launch_one(const Params& p, const Peers& peers, int row_blocks, cudaStream_t st) {
   auto kern = gemv_w4_b_kernel<DT, IK, M1>;
   auto kern_peer = gemv_w4_b_peer_kernel<DT, IK, M1>;
-  static thread_local bool attr_set = false;
+  static thread_local bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBytesB) != cudaSuccess ||
         cudaFuncSetAttribute(kern_peer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmemBytesB) != cudaSuccess) {

@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(kFThreads, 2) gemm_w4_frag_kernel(const FParam
 template <tg_dtype DT, int IK, bool HI>
 int launch_frag(const FParams& p, int rows_per_pass, int kpad, cudaStream_t st) {
   auto kern = gemm_w4_frag_kernel<DT, IK, HI>;
-  static thread_local int ctas_per_sm = 0, n_sm = 0;
+  static thread_local int ctas_per_sm_dev[kMaxDevices] = {}, n_sm = 0;
+  int& ctas_per_sm = ctas_per_sm_dev[current_device_slot()];
   const size_t smem = 8192 + (size_t)rows_per_pass * (kpad + 8) * 2;
   if (ctas_per_sm == 0) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 + kFMaxXSmem) != cudaSuccess) {
