@@ -1,6 +1,7 @@
 // extern "C" entry points of libtinygemm_b200.so: argument validation (the reference's
 // TORCH_CHECKs restated on plain sizes), format dispatch, error strings.
 // Declarations and the reference interface each one replaces: include/tinygemm_b200.h.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -30,6 +31,15 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
                         const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
                         tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st,
                         void* const* y_peers = nullptr, int n_peers = 0, int64_t y_row_stride = 0, int silu_pairs = 0);
+int launch_gemm_w4_tc_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut, const uint8_t* exps,
+                        int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik, tg_w4_format fmt, tg_dtype dt,
+                        const uint16_t* const_lut, cudaStream_t st, void* const* y_peers = nullptr, int n_peers = 0,
+                        int64_t y_row_stride = 0, int silu_pairs = 0);
+void set_tc_ctas_per_sm(int v);
+static bool use_old_b() {
+  static const bool v = getenv("TG_W4_OLD") != nullptr && atoi(getenv("TG_W4_OLD")) != 0;  // A/B switch while the tcgen05 kernel is tuned
+  return v;
+}
 int launch_gemm_w4_rm_A(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
                         const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
                         tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st);
@@ -160,6 +170,9 @@ int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_z
     rc = const_lut_for(format, dtype, (cudaStream_t)stream, &clut);
     if (rc != TG_OK) return rc;
   }
+  if (side == TG_WEIGHT_B && !use_old_b())
+    return launch_gemm_w4_tc_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
+                               (cudaStream_t)stream);
   if (side == TG_WEIGHT_B) {
     // more activation rows than the decode kernel carries per pass: fragment-order tensor-core kernel (gemv_w4_frag.cu)
     if (g_frag_min_rows > 0 && rows_x >= g_frag_min_rows) {
@@ -204,6 +217,9 @@ int tg_gemm_w4_rm_sharded(void* const* y_peers, int n_peers, int64_t y_row_strid
     rc = const_lut_for(format, dtype, (cudaStream_t)stream, &clut);
     if (rc != TG_OK) return rc;
   }
+  if (!use_old_b())
+    return launch_gemm_w4_tc_B(y_peers[0], x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
+                               clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride);
   return launch_gemm_w4_rm_B(y_peers[0], x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
                              clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride);
 }
@@ -233,6 +249,9 @@ int tg_gemm_w4_rm_silu_pairs(void* y, const void* x, const int32_t* w, const voi
     rc = const_lut_for(format, dtype, (cudaStream_t)stream, &clut);
     if (rc != TG_OK) return rc;
   }
+  if (!use_old_b())
+    return launch_gemm_w4_tc_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
+                               (cudaStream_t)stream, nullptr, 0, 0, /*silu_pairs=*/1);
   return launch_gemm_w4_rm_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
                              (cudaStream_t)stream, nullptr, 0, 0, /*silu_pairs=*/1);
 }

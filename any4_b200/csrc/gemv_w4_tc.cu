@@ -1,0 +1,1014 @@
+// B200 (sm_100a) weight-only 4-bit GEMV / small-batch GEMM on the 5th-generation tensor cores, weight in the
+// reference's "B" int4 tensor-core layout (weightOnRight = true, the Any4Linear default), 1..16 activation rows
+// in ONE pass over the weights.
+//
+// Replaces the reference path tinygemm_y_f16RM_x_f16RM_w_{int4,any4,mx4}TC ->
+// tinygemm_m16n8k16_chunk_kernel<ALayout_RM, BLayout_TC_int4> (TinyGemm_int4.cu:294-548, TinyGemmImpl.cuh:23-345,
+// MatrixLayoutB.cuh:686-1101, Dequantization.cuh:55-131).  Not a port of that gmem->register mma.sync kernel:
+//
+//  * "Lane per weight row".  A CTA works on 32 consecutive weight rows (4 n-tiles of the packed layout); lane L of
+//    every dequant warp owns row row_of_lane(L).  The row's 16-entry LUT is expanded once per row block into a
+//    256-entry byte-PAIR table  pair[b] = (LUT[b & 15], LUT[b >> 4])  stored bank-private in shared memory
+//    (entry e of lane L at e*256 + 4L), so both nibbles of a packed byte are dequantised by ONE conflict-free
+//    LDS.32 whose address is ONE PRMT.  Group scale/zero: one fma.rn.{bf16,f16}x2 per pair - the same single-rounded
+//    FMA as the reference (MatrixLayoutB.cuh:1042-1046), hence bit-identical dequantised weights.
+//  * The dequantised bf16/fp16 pairs never touch shared memory or mma.sync registers: each thread writes its row's
+//    k-slice straight into TENSOR MEMORY with tcgen05.st (32x32b: thread = TMEM lane = weight row, 8 columns = one
+//    K = 16 step), and ONE elected thread issues tcgen05.mma (M = 128, N = 4 * MB, K = 16, kind::f16, fp32
+//    accumulators in TMEM) with A read from TMEM and the activations read from shared memory through a K-major
+//    no-swizzle descriptor.  The four warps of a "quad" own the four 32-lane TMEM sub-partitions; all four work on
+//    the SAME 32 weight rows but on different 128-wide k chunks, and the activation operand is block structured:
+//    operand column 4*mi + j carries activation row mi for the k chunk of quarter j, so accumulator element
+//    (lane 32j + L, column 4*mi + j) is the partial dot product of lane L's row over quarter j's chunk.  The other
+//    columns of a lane hold cross terms nobody reads.  One pass therefore handles 16 activation rows (N = 64).
+//  * Weights stream HBM -> shared memory with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx, 4 KiB copies,
+//    L2 evict-first) into a 3 x 16 KiB ring fed by a producer thread.  The activations are staged per ring stage by
+//    dedicated warps (global -> PRMT k-permutation -> the operand layout the descriptor describes); nothing about k
+//    or m has to fit shared memory, so any k works.
+//  * Work decomposition is stream-K over (row block, 128-k chunk) units: CTA i of G processes the contiguous unit
+//    range [i*U/G, (i+1)*U/G).  A row block cut by a range boundary is finished by the LAST of its CTAs to arrive
+//    (fp32 partials in a device workspace, arrival counter, summed in CTA order: deterministic).
+//  * The CTA needs 113 KB of shared memory, 256 TMEM columns and <= 80 registers x 384 threads, so TWO CTAs - of the
+//    same GEMV or of two consecutive GEMVs of a stream (programmatic dependent launch) - share an SM: the prologue,
+//    first-byte latency and row-block boundaries of one hide under the dequant of the other.  With
+//    TG_OPT_STATIC_WEIGHTS the weight stream, the table build and the dequant of the first TMEM slots start before
+//    the previous kernel has finished; only the activation staging (and with it every MMA and store) waits.
+//
+// Numerics: dequantised weights bit-identical to the reference; products exact; fp32 accumulation in the tensor
+// core (order differs from the reference, as allowed by SURVEY.md 3.6); one RN at the end.  A non-finite weight
+// only reaches its own row's sums (the cross terms it pollutes are never read), as in the reference.
+#include <atomic>
+#include <cstdlib>
+#include <type_traits>
+
+#include "common.cuh"
+#include "w4_common.cuh"
+
+namespace tg {
+namespace tc {
+using namespace w4;
+
+constexpr int kDqWarps = 8;                 // dequant warps: quad Q = warp / 4, quarter j = warp % 4
+constexpr int kDqThreads = kDqWarps * 32;
+constexpr int kWStages = 3;                 // weight ring depth
+constexpr uint32_t kTileBytes = 4096;       // one n-tile (8 rows) x 1024 k of packed weights = one bulk copy
+constexpr uint32_t kWStageStride = 4 * kTileBytes + 128;  // + room for the bank staggers of tiles 1..3
+constexpr uint32_t kRegionA = 65536;        // pair table (even 128-B half-lines) + odd half-lines (see odd_hl)
+constexpr uint32_t kWRingOff = kRegionA;
+constexpr uint32_t kXDenseOff = kWRingOff + kWStages * kWStageStride;  // activation ring of the MB >= 8 kernels
+constexpr uint32_t kSmemBase = 0x400;       // shared-window address of the dynamic shared memory (no static smem): see lds_table
+constexpr int kCtrlHl = 240;                // odd half-lines 240.. hold the mbarriers and the TMEM base address
+constexpr int kMaxGrid = 512;
+constexpr int kWsPools = 4;
+
+// split fix-up workspace (see finish_partial): fp32 partial sums [pool][CTA][slot 0/1][mi][row] and arrival counters
+__device__ float g_ws_partial[kWsPools][kMaxGrid * 2 * 16 * 32];
+__device__ unsigned g_ws_counter[kWsPools][kMaxGrid];
+
+struct ParamsTC {
+  const uint8_t* w;      // packed weight
+  const uint16_t* x;     // [m][k]
+  uint16_t* y;           // [m][y_stride]
+  const uint32_t* sz;    // [k/g][w_rows] (scale, zero) pairs, null for mx4
+  const uint8_t* exps;   // [w_rows][k/g] e8m0, mx4 only
+  const uint16_t* lut;   // [16] or [w_rows][16]
+  float* ws_partial;     // this launch's workspace pool
+  unsigned* ws_counter;
+  int64_t tile_stride;   // bytes between consecutive n-tiles of the packed weight = 4 * k
+  int64_t y_stride;
+  int lut_stride;        // 0 or 16
+  int m;                 // activation rows of this launch (<= MB)
+  int w_rows;            // padded weight rows (multiple of 8)
+  int k;
+  int glog2;             // log2(group)
+  int chunks_per_row;    // C = ceil(k / 128)
+  int ug;                // chunks per work unit: 1 (stream-K over chunks) or C (whole row blocks per CTA)
+  int cq, cr;            // units per CTA: U / G and U % G
+  int flags;             // bit 3: static weights; bit 4: silu(gate)*up over interleaved row pairs
+#ifdef TG_W4_TRACE
+  unsigned long long* trace;  // [CTAs][64] globaltimer stamps (scripts/trace_tc.py)
+#endif
+};
+#ifdef TG_W4_TRACE
+#define TC_TRACE(slot)                                                           \
+  do {                                                                           \
+    if (p.trace != nullptr) {                                                    \
+      unsigned long long t__;                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                    \
+      p.trace[(size_t)blockIdx.x * 64 + (slot)] = t__;                           \
+    }                                                                            \
+  } while (0)
+#else
+#define TC_TRACE(slot) \
+  do {                 \
+  } while (0)
+#endif
+
+// ---- geometry of the packed B int4 layout [n/8][k/(ik*16)][32][ik/2] (TinyGemmConvertB.cu:252-308) inside one
+// 128-k chunk of one row: four 16-byte units of four words; word (tp, q) holds k-slot q (k0 = 2q) of tiles 2tp, 2tp+1:
+//   byte 0 = tile 2tp (k0 | k0+8), byte 1 = tile 2tp+1 (k0 | k0+8), byte 2 = tile 2tp (k0+1 | k0+9), byte 3 = tile 2tp+1
+template <int IK>
+struct Geo;
+template <>
+struct Geo<4> {  // chunk = [2 super-tiles][32 lanes][2 words]; row g at +g*32 inside each 256 B
+  static constexpr int kRowStride = 32;
+  static constexpr int kStagger = 16;
+  __device__ static constexpr int unit_off(int u) { return (u >> 1) * 256 + (u & 1) * 16; }
+  __device__ static constexpr int unit_of(int tp, int q) { return (tp >> 1) * 2 + (q >> 1); }
+  __device__ static constexpr int word_of(int tp, int q) { return (q & 1) * 2 + (tp & 1); }
+};
+template <>
+struct Geo<2> {  // chunk = [4 super-tiles][32 lanes][1 word]; row g at +g*16 inside each 128 B
+  static constexpr int kRowStride = 16;
+  static constexpr int kStagger = 64;
+  __device__ static constexpr int unit_off(int u) { return u * 128; }
+  __device__ static constexpr int unit_of(int tp, int) { return tp; }
+  __device__ static constexpr int word_of(int, int q) { return q; }
+};
+template <>
+struct Geo<8> {  // chunk = [1 super-tile][32 lanes][4 words]; row g at +g*64
+  static constexpr int kRowStride = 64;
+  static constexpr int kStagger = 32;
+  __device__ static constexpr int unit_off(int u) { return u * 16; }
+  __device__ static constexpr int unit_of(int, int q) { return q; }
+  __device__ static constexpr int word_of(int tp, int) { return tp; }
+};
+// Bank conflicts of the 16-byte weight loads: a quarter-warp (8 lanes) is served per wavefront and the 8 rows of ONE
+// n-tile sit 16*IK/2 bytes apart, so rows j and j+4 collide.  Hence lane L owns row L with bits 2 and 3 swapped (a
+// quarter-warp holds rows 4h..4h+3 of TWO tiles) and the odd tile of each pair is staged kStagger bytes further.
+// ik = 8 additionally rotates the unit order of half the lanes (rows 64 B apart).
+__device__ __forceinline__ int row_of_lane(int l) { return (l & 0x13) | ((l & 4) << 1) | ((l & 8) >> 1); }
+template <int IK>
+__device__ __forceinline__ uint32_t tile_off(int t) {
+  return (uint32_t)t * kTileBytes + (uint32_t)((t + 1) >> 1) * Geo<IK>::kStagger;
+}
+
+__device__ __forceinline__ uint32_t odd_hl(int hl) { return (uint32_t)hl * 256u + 128u; }
+// mbarrier i (8 bytes each, 16 per half-line)
+__device__ __forceinline__ uint32_t bar_off(int i) { return odd_hl(kCtrlHl + (i >> 4)) + (uint32_t)(i & 15) * 8u; }
+enum : int { B_WFULL = 0, B_WEMPTY = 3, B_AFULL = 6, B_AEMPTY = 9, B_DFULL = 12, B_DEMPTY = 14, B_COUNT = 16 };
+constexpr uint32_t kHolderOff = 242u * 256u + 128u;  // TMEM base address; +4: "this CTA is the last arriver" flag
+
+template <int MB>
+struct Cfg {
+  static constexpr int N = 4 * MB;                 // MMA N: operand column 4*mi + j
+  static constexpr int NS = 3;                     // TMEM A slots (64 columns = one 128-k chunk per quarter), shared by the quads
+  static constexpr int NB = MB == 16 ? 1 : 2;      // accumulator buffers
+  static constexpr int NX = 3;                     // activation ring depth
+  static constexpr int NIT = MB == 4 ? 4 : MB;     // 8-byte activation pieces a dequant thread stages per ring stage (max)
+  static constexpr int XR = MB == 4 ? 8 : 2 * MB;  // register ring of pieces in flight: XR / pieces-per-stage stages ahead
+  static constexpr int kWarps = 10;                // 8 dequant, TMA producer, MMA issuer
+  static constexpr int kThreads = kWarps * 32;
+  static constexpr int kABase = NB * N;            // TMEM: accumulators first, then the A slots
+  static constexpr int kRedHl0 = MB == 4 ? 192 : 0;  // reduction scratch [4][MB] half-lines
+  static constexpr uint32_t kXStageBytes = MB == 4 ? 64u * 256u : 32u * (MB / 2) * 128u;
+  static constexpr uint32_t kSmem = MB == 4 ? kXDenseOff : kXDenseOff + NX * kXStageBytes;
+  static constexpr int kMinBlocks = MB == 4 ? 2 : 1;
+};
+static_assert(Cfg<4>::kSmem <= 115712u, "two CTAs of the decode kernel must fit one SM");
+static_assert(Cfg<16>::kSmem <= 232448u, "exceeds the 227 KiB opt-in shared memory of sm_100");
+static_assert(Cfg<16>::kABase + 3 * 64 <= 256 && Cfg<8>::kABase + 3 * 64 <= 256, "TMEM budget");
+
+// ---- small PTX wrappers ----
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// A try_wait costs ~200 cycles even on a completed phase (scripts/microbench/tc_probe2.cu), so every lane waits
+// itself (no poll-then-confirm) and the kernel is organised around as few waits per ring stage as possible.
+__device__ __forceinline__ void wait_all(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t addr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void tc_mma(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p; }" ::"r"(d),
+               "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// pair-table lookup: the dynamic shared window of a kernel without static shared memory starts at kSmemBase (checked
+// at kernel entry), so the table base is an immediate and a lookup is PRMT + LDS.  Not volatile: a pure function of
+// the index between two table builds (its index always comes from a weight load behind the build's barrier).
+__device__ __forceinline__ uint32_t lds_table(uint32_t idx) {
+  uint32_t v;
+  asm("ld.shared.b32 %0, [%1+%2];" : "=r"(v) : "r"(idx), "n"(kSmemBase));
+  return v;
+}
+template <bool PEERS>
+__device__ __forceinline__ void store_out(uint16_t* y, const Peers& peers, int64_t idx, uint16_t v) {
+  if constexpr (PEERS) {
+#pragma unroll 1
+    for (int r = 0; r < peers.n; ++r) peers.y[r][idx] = v;  // the same location in every rank's symmetric buffer
+  } else {
+    y[idx] = v;
+  }
+}
+
+// CTA i of the grid owns units [begin, end) (in 128-k chunks): the first cr CTAs get cq + 1 units of ug chunks
+__device__ __forceinline__ void cta_range(const ParamsTC& p, int i, int& begin, int& end) {
+  begin = (i * p.cq + min(i, p.cr)) * p.ug;
+  end = begin + (p.cq + (i < p.cr ? 1 : 0)) * p.ug;
+}
+__device__ __forceinline__ int cta_of_chunk(const ParamsTC& p, int u) {  // split mode only (ug == 1)
+  const int big = p.cr * (p.cq + 1);
+  return u < big ? u / (p.cq + 1) : p.cr + (u - big) / p.cq;
+}
+
+// Cursor over the CTA's ring stages: segments (one per row block touched), 8 chunks per stage.
+struct StageIt {
+  int c, cin, len, st, rb;
+  __device__ __forceinline__ void init(int c_begin, int c_end, int Cn) {
+    c = c_begin;
+    rb = c_begin / Cn;
+    cin = c_begin - rb * Cn;
+    len = min(Cn - cin, c_end - c);
+    st = 0;
+  }
+  __device__ __forceinline__ bool valid(int c_end) const { return c < c_end; }
+  __device__ __forceinline__ int cs() const { return cin + st * 8; }   // first chunk (within the row) of the stage
+  __device__ __forceinline__ int rem() const { return len - st * 8; }  // chunks left in the segment (stage: min(8, rem))
+  __device__ __forceinline__ void next(int c_end, int Cn) {
+    if ((st + 1) * 8 < len) {
+      ++st;
+    } else {
+      c += len;
+      cin = 0;
+      st = 0;
+      ++rb;
+      len = min(Cn, c_end - c);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// kernel: grid = G CTAs (1-D), block = 10 warps
+//   warps 0..7  dequant: quad Q = w / 4, quarter j = w % 4; warp w dequantises chunk w of every ring stage (8 chunks)
+//               into TMEM lanes 32j.. of A slot (2 * stage + Q) % 3, and stages its share of the activations
+//   warp 8      bulk-TMA producer of the weight ring
+//   warp 9      MMA issuer (one elected lane): per stage and quad 8 x tcgen05.mma + commit
+// Ordering without extra barriers: a warp stores its pieces of stage i+1's activations BEFORE it signals its A slot
+// of stage i, and the issuer starts stage i+1 only after it has seen all eight A-slot signals of stage i; an A slot
+// is refilled only after the commit of its previous use, which (one issuer: commits are cumulative) also proves that
+// the MMAs of stage i-2 are done, i.e. that activation ring slot (i+1) % 3 is free.
+// ---------------------------------------------------------------------------------------
+template <tg_dtype DT, int IK, int MB, bool PEERS>
+__device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& peers) {
+  using C = Cfg<MB>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+
+  // Programmatic dependent launch: the next kernel of the stream may become resident as soon as all our CTAs have
+  // started.  We wait for the previous kernel before touching anything it may have produced; weights, LUTs and
+  // scales may be declared static by the caller (TG_OPT_STATIC_WEIGHTS), in which case only the activation staging
+  // (and with it every MMA and store) is ordered behind it.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const bool static_w = (p.flags & 8) != 0;
+  if (threadIdx.x == 0) TC_TRACE(0);
+  if (sbase != kSmemBase) __trap();  // lds_table() relies on it
+  if (!static_w) griddep_wait();
+
+  int c_begin, c_end;
+  cta_range(p, (int)blockIdx.x, c_begin, c_end);
+  const int Cn = p.chunks_per_row;
+  const int rb_first = c_begin / Cn;
+  const int n_groups = p.k >> p.glog2;
+  const bool is_mx4 = p.sz == nullptr;
+
+  // activation operand geometry.  K step s of a ring stage (s = Q*8 + T: quad Q, k-tile T of the chunk) reads operand
+  // rows n = 4*mi + j (activation row mi, quarter j -> chunk Q*4 + j of the stage), 16 K values each:
+  //   K index 2c + f  <->  k = 16*tile + c + 8f      (the order the packed bytes dequantise in)
+  // 16-byte unit (s, h, n) = K indices 8h..8h+7.  Placement (the strides are what the descriptor is told):
+  //   MB = 4, m = 1 : s*256 + h*64 + j*16          in the odd half-lines of region A (rows 4.. alias the other half)
+  //   MB = 4, m >= 2: ((s*2 + h)*G8 + n/8)*256 + (n%8)*16,  G8 = 1 (m = 2) or 2
+  //   MB >= 8       : ((s*2 + h)*G8 + n/8)*128 + (n%8)*16 in the dense ring, G8 = MB / 2
+  const bool x_single = MB == 4 && p.m == 1;
+  const uint32_t x_g8 = MB == 4 ? (p.m > 2 ? 2u : 1u) : (uint32_t)(MB / 2);
+  const uint32_t x_pitch = MB == 4 ? 256u : 128u;
+  const uint32_t x0 = sbase + (MB == 4 ? 128u : kXDenseOff);
+
+  // ------------------------------------------------------------------ setup
+  StageIt pit;  // producer cursor (warp 8)
+  pit.init(c_begin, c_end, Cn);
+  uint32_t pseq = 0;
+  uint64_t pol = 0;
+  // one ring stage: lane 0 arms the barrier, lanes 0..3 issue one 4 KiB n-tile copy each
+  auto produce = [&]() {
+    const int s = (int)(pseq % kWStages);
+    const int rb = pit.rb;
+    const int tiles_valid = min(32, p.w_rows - rb * 32) >> 3;
+    const int nvalid = min(8, pit.rem());
+    const int k0 = pit.cs() * 128;
+    const uint32_t bytes = (uint32_t)min(nvalid * 128, p.k - k0) * 4u;  // per n-tile: 8 rows * k / 2
+    const uint32_t bar = sbase + bar_off(B_WFULL + s);
+    if (lane == 0) mbar_expect_tx(bar, bytes * (uint32_t)tiles_valid);
+    __syncwarp();
+    if (lane < tiles_valid)
+      bulk_g2s(sbase + kWRingOff + (uint32_t)s * kWStageStride + tile_off<IK>(lane),
+               p.w + (int64_t)(rb * 4 + lane) * p.tile_stride + (int64_t)k0 * 4, bytes, bar, pol);
+    if (lane == 0 && pseq < 3) TC_TRACE(17 + pseq);
+    ++pseq;
+    pit.next(c_end, Cn);
+  };
+  uint4 lut0 = make_uint4(0, 0, 0, 0), lut1 = lut0;
+  uint32_t lut_hi[2] = {0u, 0u};
+  const int rl = row_of_lane(lane);  // the weight row (within the block) this lane owns
+  auto load_lut = [&](int rb) {
+    const int row = min(rb * 32 + rl, p.w_rows - 1);
+    const uint16_t* lrow = p.lut + (int64_t)row * p.lut_stride;
+    lut0 = *reinterpret_cast<const uint4*>(lrow);
+    lut1 = *reinterpret_cast<const uint4*>(lrow + 8);
+    lut_hi[0] = (uint32_t)lrow[2 * warp];  // this warp builds the 32 table entries whose high nibble is 2w, 2w+1
+    lut_hi[1] = (uint32_t)lrow[2 * warp + 1];
+  };
+
+  if (warp == kDqWarps) {
+    if (lane == 0) {
+      for (int i = 0; i < 3; ++i) {
+        mbar_init(sbase + bar_off(B_WFULL + i), 1);
+        mbar_init(sbase + bar_off(B_WEMPTY + i), kDqWarps);
+        mbar_init(sbase + bar_off(B_AFULL + i), 4);
+        mbar_init(sbase + bar_off(B_AEMPTY + i), 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(sbase + bar_off(B_DFULL + i), 1);
+        mbar_init(sbase + bar_off(B_DEMPTY + i), 4);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      TC_TRACE(16);
+    }
+    __syncwarp();
+    // the weight stream starts right here: the ring has kWStages free stages, nobody has to be asked
+    pol = l2_evict_first_policy();
+    for (int i = 0; i < kWStages && pit.valid(c_end); ++i) produce();
+  } else if (warp == kDqWarps + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kHolderOff), "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    load_lut(rb_first);  // in flight across the setup barrier
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<const volatile uint32_t*>(smem + kHolderOff);
+  if (threadIdx.x == 0) TC_TRACE(1);
+
+  if (warp < kDqWarps) {
+    // =============================================================== dequant warps
+    const int Q = warp >> 2, j = warp & 3;
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+    const uint32_t wl_off = kWRingOff + tile_off<IK>(rl >> 3) + (uint32_t)warp * 512u + (uint32_t)(rl & 7) * Geo<IK>::kRowStride;
+    const uint32_t my_tmem = tmem + ((uint32_t)(j * 32) << 16);
+    uint32_t gst = 0;   // ring stage counter of the CTA (weight ring slot gst % 3, A slot use 2 * gst + Q)
+    uint32_t dseq = 0;  // row blocks (accumulator buffer dseq % NB)
+    bool first_seg = true;
+
+    // Small global loads issued while the weight ring is full come back only after everything queued in front of
+    // them (~2 us for 96 KB per SM), so the per-stage operands - group (scale, zero) words and activation pieces -
+    // travel through REGISTER RINGS filled several stages ahead: a stage consumes the head, shifts, and requests
+    // the stage `depth` ahead at the tail.  Depth = ring size / values per stage (switch on the runtime count).
+
+    // ---- group words: nsz per stage (1: group >= 128, 2: group 64, 4: group 32), ring of 8 -> 8 / 4 / 2 stages ----
+    const int nsz = p.glog2 >= 7 ? 1 : (p.glog2 == 6 ? 2 : 4);
+    uint32_t szr[8];
+    StageIt zl;
+    zl.init(c_begin, c_end, Cn);
+    auto sz_word = [&](int t, int n) -> uint32_t {  // word t of n for this warp's chunk of stage zl
+      if (!zl.valid(c_end) || warp >= zl.rem()) return 0u;
+      const int row = min(zl.rb * 32 + rl, p.w_rows - 1);
+      const int gi = min(((zl.cs() + warp) * 128 + t * (128 / n)) >> p.glog2, n_groups - 1);
+      return is_mx4 ? (e8m0_to_dt<DT>((uint32_t)p.exps[(int64_t)row * n_groups + gi]) | 0x80000000u)  // zero = -0
+                    : p.sz[(int64_t)gi * p.w_rows + row];
+    };
+    auto sz_fill = [&](auto n_) {  // prologue: the first 8 / n stages
+      constexpr int n = decltype(n_)::value;
+#pragma unroll
+      for (int d = 0; d < 8 / n; ++d) {
+#pragma unroll
+        for (int t = 0; t < n; ++t) szr[d * n + t] = sz_word(t, n);
+        zl.next(c_end, Cn);
+      }
+    };
+    // consume this stage's words into (s, s) / (z, z) pairs for the four 32-k quarters, shift, request the tail stage
+    auto sz_step = [&](auto n_, uint32_t (&s2)[4], uint32_t (&z2)[4]) {
+      constexpr int n = decltype(n_)::value;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t v = szr[t * n / 4];
+        s2[t] = prmt(v, v, 0x1010u);  // mx4 words carry zero = -0: fma(v, s, -0) == v * s incl. sign of zero
+        z2[t] = prmt(v, v, 0x3232u);
+      }
+#pragma unroll
+      for (int i = 0; i + n < 8; ++i) szr[i] = szr[i + n];
+#pragma unroll
+      for (int t = 0; t < n; ++t) szr[8 - n + t] = sz_word(t, n);
+      zl.next(c_end, Cn);
+    };
+
+    // ---- activation staging: thread (warp w, lane) owns the 8-byte pieces f of the units (s = 2w + slo, h, n) ----
+    // lane = f | j<<1 | (h or mi&1)<<3 | slo<<4: a half-warp writes one contiguous 128-byte half-line (conflict free)
+    // and reads whole 32-byte sectors of x.  Pieces per stage: 1 (m = 1), 2 (m = 2), 4 (m = 3, 4), MB (MB >= 8).
+    StageIt xl, xs;
+    xl.init(c_begin, c_end, Cn);
+    xs = xl;
+    uint32_t xs_seq = 0;
+    uint2 xr[C::XR];
+    const int x_f = lane & 1, x_j = (lane >> 1) & 3, x_b3 = (lane >> 3) & 1, x_s = 2 * warp + (lane >> 4);
+    const int x_ch = (x_s >> 3) * 4 + x_j;                     // chunk of the stage
+    const int x_koff = x_ch * 128 + (x_s & 7) * 16 + 8 * x_f;  // + 4h
+    const int x_nit = x_single ? 1 : 2 * (int)x_g8;
+    auto x_piece = [&](int it) -> uint2 {  // piece `it` of stage xl
+      const int h = x_single ? x_b3 : (it & 1);
+      const int mi = x_single ? 0 : (it >> 1) * 2 + x_b3;
+      const int kk = xl.cs() * 128 + x_koff + 4 * h;
+      if (xl.valid(c_end) && x_ch < xl.rem() && kk < p.k && mi < p.m)
+        return *reinterpret_cast<const uint2*>(p.x + (int64_t)mi * p.k + kk);
+      return make_uint2(0u, 0u);
+    };
+    auto x_fill = [&](auto n_) {
+      constexpr int n = decltype(n_)::value;
+#pragma unroll
+      for (int d = 0; d < C::XR / n; ++d) {
+#pragma unroll
+        for (int it = 0; it < n; ++it) xr[d * n + it] = x_piece(it);
+        xl.next(c_end, Cn);
+      }
+    };
+    // store the head stage's pieces into activation ring slot xs_seq % NX, shift, request the tail stage
+    auto x_step = [&](auto n_) {
+      constexpr int n = decltype(n_)::value;
+      if (xs.valid(c_end)) {
+        const uint32_t xb = x0 + (xs_seq % C::NX) * C::kXStageBytes;
+#pragma unroll
+        for (int it = 0; it < n; ++it) {
+          // lane f = 0 holds x[k0 + 4h ..+3], lane f = 1 holds x[k0 + 8 + 4h ..+3]; unit = (lo0,hi0,lo1,hi1,lo2,hi2,lo3,hi3):
+          // lane 0 writes the first 8 bytes (needs the partner's .x), lane 1 the last 8 (needs the partner's .y)
+          const uint32_t got = __shfl_xor_sync(0xffffffffu, x_f ? xr[it].x : xr[it].y, 1);
+          const uint32_t a = x_f ? got : xr[it].x, b = x_f ? xr[it].y : got;
+          uint32_t dst;
+          if (x_single) {
+            dst = xb + (uint32_t)x_s * 256u + (uint32_t)x_b3 * 64u + (uint32_t)x_j * 16u + (uint32_t)x_f * 8u;
+          } else {
+            const uint32_t h = it & 1, grp = it >> 1;
+            dst = xb + ((uint32_t)(x_s * 2 + h) * x_g8 + grp) * x_pitch + (uint32_t)(x_b3 * 4 + x_j) * 16u + (uint32_t)x_f * 8u;
+          }
+          sts64(dst, prmt(a, b, 0x5410u), prmt(a, b, 0x7632u));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+        ++xs_seq;
+        xs.next(c_end, Cn);
+      }
+#pragma unroll
+      for (int i = 0; i + n < C::XR; ++i) xr[i] = xr[i + n];
+#pragma unroll
+      for (int it = 0; it < n; ++it) xr[C::XR - n + it] = x_piece(it);
+      xl.next(c_end, Cn);
+    };
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using I4 = std::integral_constant<int, 4>;
+    using IM = std::integral_constant<int, MB>;
+    auto x_fill_any = [&]() {
+      if constexpr (MB == 4) {
+        if (x_nit == 1) x_fill(I1{});
+        else if (x_nit == 2) x_fill(I2{});
+        else x_fill(I4{});
+      } else {
+        x_fill(IM{});
+      }
+    };
+    auto x_step_any = [&]() {
+      if constexpr (MB == 4) {
+        if (x_nit == 1) x_step(I1{});
+        else if (x_nit == 2) x_step(I2{});
+        else x_step(I4{});
+      } else {
+        x_step(IM{});
+      }
+    };
+    if (nsz == 1) sz_fill(I1{});
+    else if (nsz == 2) sz_fill(I2{});
+    else sz_fill(I4{});
+
+    int c = c_begin, rb = rb_first, cin = c_begin - rb_first * Cn;
+    while (c < c_end) {
+      const int len = min(Cn - cin, c_end - c);
+      const int nst = (len + 7) >> 3;
+      const int row0 = rb * 32;
+
+      // ---- pair table of this row block ----
+      {
+        const uint32_t tp_[8] = {lut0.x, lut0.y, lut0.z, lut0.w, lut1.x, lut1.y, lut1.z, lut1.w};
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t dst = sbase + (uint32_t)((2 * warp + hh) * 16) * 256u + lane4;
+#pragma unroll
+          for (int lo = 0; lo < 16; ++lo)
+            sts32(dst + (uint32_t)lo * 256u, prmt(tp_[lo >> 1], lut_hi[hh], (lo & 1) ? 0x5432u : 0x5410u));
+        }
+      }
+      if (c + len < c_end) load_lut(rb + 1);  // the next row block's LUT rows: a whole row block of time to arrive
+      if (first_seg) {
+        // the activations are the previous kernel's output: everything up to here overlapped its tail
+        if (static_w) griddep_wait();
+        x_fill_any();
+        x_step_any();                  // stage 0's activations
+        bar_sync(2, kDqThreads + 32);  // with the issuer warp: they are complete
+      }
+      bar_sync(1, kDqThreads);
+      if (threadIdx.x == 0 && first_seg) TC_TRACE(2);
+
+      for (int st = 0; st < nst; ++st, ++gst) {
+        const int nvalid = min(8, len - st * 8);
+        const bool valid = warp < nvalid;
+        const int kt_valid = (p.k - (cin + st * 8 + warp) * 128) >> 4;  // k-tiles of this warp's chunk that exist (>= 8: all)
+        const int s = (int)(gst % kWStages);
+        uint32_t s2[4], z2[4];
+        if (nsz == 1) sz_step(I1{}, s2, z2);
+        else if (nsz == 2) sz_step(I2{}, s2, z2);
+        else sz_step(I4{}, s2, z2);
+
+        const uint32_t use = 2u * gst + (uint32_t)Q;  // A slot use (every stage serves both quads, see below)
+        const uint32_t acol = my_tmem + (uint32_t)(C::kABase + (int)(use % C::NS) * 64);
+        const uint32_t wb = sbase + wl_off + (uint32_t)s * kWStageStride;
+        wait_all(sbase + bar_off(B_WFULL + s), (gst / kWStages) & 1u);
+        if (threadIdx.x == 0 && gst < 4) TC_TRACE(21 + gst * 4);
+
+        // one k-tile (K step) of this lane's row: 8 byte lookups -> 8 TMEM columns
+        auto k_step = [&](const uint32_t (&W)[4][4], int T, uint32_t (&r)[8]) {
+          const int tp = T >> 1, b = T & 1;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t w = W[Geo<IK>::unit_of(tp, q)][Geo<IK>::word_of(tp, q)];
+            // column 2q: byte b = (k0 | k0+8), column 2q+1: byte b+2 = (k0+1 | k0+9) of k-tile T
+            r[2 * q] = lds_table(prmt(w, lane4, 0x7604u | (uint32_t)(b << 4)));
+            r[2 * q + 1] = lds_table(prmt(w, lane4, 0x7604u | (uint32_t)((b + 2) << 4)));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) r[i] = fma2<DT>(r[i], s2[tp], z2[tp]);
+        };
+        auto slot_wait = [&]() {  // the slot's previous use has been consumed (and with it all MMAs of stage gst - 2)
+          if (use >= (uint32_t)C::NS) {
+            wait_all(sbase + bar_off(B_AEMPTY + (int)(use % C::NS)), ((use / C::NS) - 1u) & 1u);
+            tc_fence_after();
+          }
+        };
+        if (valid && kt_valid >= 8) {
+          // the common case, straight-line: 4 x LDS.128, then per k-tile 8 x (PRMT, LDS.32, HFMA2) + one tcgen05.st
+          uint32_t W[4][4];
+          if constexpr (IK == 8) {
+            // lanes whose k-slot id bit 1 is set take their units one step ahead (bank-conflict-free 16-byte loads)
+            const int sh = (lane >> 1) & 1;
+            uint4 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r[u] = lds128(wb + (uint32_t)(((u + sh) & 3) * 16));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // logical unit u was loaded at step (u - sh) & 3
+              const uint4 a = r[u], b = r[(u + 3) & 3];
+              W[u][0] = sh ? b.x : a.x, W[u][1] = sh ? b.y : a.y, W[u][2] = sh ? b.z : a.z, W[u][3] = sh ? b.w : a.w;
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint4 v = lds128(wb + (uint32_t)Geo<IK>::unit_off(u));
+              W[u][0] = v.x, W[u][1] = v.y, W[u][2] = v.z, W[u][3] = v.w;
+            }
+          }
+          uint32_t r0[8];
+          k_step(W, 0, r0);  // overlaps the wait for the TMEM slot
+          slot_wait();
+          tmem_st8(acol, r0);
+#pragma unroll
+          for (int T = 1; T < 8; ++T) {
+            uint32_t r[8];
+            k_step(W, T, r);
+            tmem_st8(acol + (uint32_t)(T * 8), r);
+          }
+        } else {
+          // partial / missing chunk (segment tail, k tail): compact code, exact zeros where nothing exists.  A stage
+          // always serves both quads (uniform slot sequence), so a quad without chunks just writes zeros.
+          slot_wait();
+#pragma unroll 1
+          for (int T = 0; T < 8; ++T) {
+            uint32_t r[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (valid && T < kt_valid) {
+              const int tp = T >> 1, b = T & 1;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                int unit, word;
+                if constexpr (IK == 4) unit = (tp >> 1) * 2 + (q >> 1), word = (q & 1) * 2 + (tp & 1);
+                else if constexpr (IK == 2) unit = tp, word = q;
+                else unit = q, word = tp;
+                const uint32_t w = lds32(wb + (uint32_t)(Geo<IK>::unit_off(unit) + 4 * word));
+                r[2 * q] = lds_table(prmt(w, lane4, 0x7604u | (uint32_t)(b << 4)));
+                r[2 * q + 1] = lds_table(prmt(w, lane4, 0x7604u | (uint32_t)((b + 2) << 4)));
+              }
+              const uint32_t sv = tp == 0 ? s2[0] : tp == 1 ? s2[1] : tp == 2 ? s2[2] : s2[3];
+              const uint32_t zv = tp == 0 ? z2[0] : tp == 1 ? z2[1] : tp == 2 ? z2[2] : z2[3];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[i] = fma2<DT>(r[i], sv, zv);
+            }
+            tmem_st8(acol + (uint32_t)(T * 8), r);
+          }
+        }
+        x_step_any();  // stage gst+1's activations: their ring slot is free (see the kernel comment)
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(sbase + bar_off(B_AFULL + (int)(use % C::NS)));
+          mbar_arrive(sbase + bar_off(B_WEMPTY + s));  // hand the weight stage back to the producer
+        }
+        if (threadIdx.x == 0 && gst < 4) TC_TRACE(22 + gst * 4);
+      }
+      if (threadIdx.x == 0 && first_seg) TC_TRACE(11);
+
+      // ---- accumulators -> red[j][mi][lane] (quad 0's warps cover the four TMEM sub-partitions) ----
+      if (Q == 0) {
+        const int buf = (int)(dseq % C::NB);
+        wait_all(sbase + bar_off(B_DFULL + buf), (dseq / C::NB) & 1u);
+        tc_fence_after();
+        if (threadIdx.x == 0 && first_seg) TC_TRACE(12);
+        const uint32_t dcol = my_tmem + (uint32_t)(buf * C::N + j);
+        uint32_t v[MB];
+#pragma unroll
+        for (int mi = 0; mi < MB; ++mi)
+          if (mi < p.m) v[mi] = tmem_ld1(dcol + (uint32_t)(mi * 4));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int mi = 0; mi < MB; ++mi)
+          if (mi < p.m) sts32(sbase + odd_hl(C::kRedHl0 + j * MB + mi) + lane4, v[mi]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sbase + bar_off(B_DEMPTY + buf));
+      }
+      ++dseq;
+      bar_sync(1, kDqThreads);
+
+      // ---- row sums: thread idx -> (mi, row); the four quarters' partials added in order ----
+      const bool complete = (cin == 0 && len == Cn);
+      const int rows_valid = min(32, p.w_rows - row0);
+      auto emit = [&](int mi, int rr, float total) {
+        if (p.flags & 16) {  // (gate, up) row pairs -> silu(gate) * up
+          const uint32_t mine = f32_to_dt<DT>(total);
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+          if (!(rr & 1) && rr < rows_valid)
+            store_out<PEERS>(p.y, peers, (int64_t)mi * p.y_stride + ((row0 + rr) >> 1), silu_mul_dt<DT>((uint16_t)mine, (uint16_t)other));
+        } else if (rr < rows_valid) {
+          store_out<PEERS>(p.y, peers, (int64_t)mi * p.y_stride + row0 + rr, f32_to_dt<DT>(total));
+        }
+      };
+      auto block_sum = [&](int mi, int rr) {
+        const uint32_t a = sbase + odd_hl(C::kRedHl0 + mi) + (uint32_t)row_of_lane(rr) * 4u;
+        float total = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) total += __uint_as_float(lds32(a + (uint32_t)(q * MB) * 256u));
+        return total;
+      };
+      if (complete) {
+        for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) emit(idx >> 5, idx & 31, block_sum(idx >> 5, idx & 31));
+      } else {
+        // Row block shared with other CTAs: publish the fp32 partials, count arrivals; the last CTA to arrive adds
+        // the partials of all the block's CTAs in CTA order (deterministic) and stores the result.  Release /
+        // acquire at GPU scope on the counter (cumulative over the CTA barriers) orders the partials.
+        const int me = (int)blockIdx.x;
+        const int slot = rb == rb_first ? 0 : 1;
+        float* mine = p.ws_partial + ((size_t)(me * 2 + slot) * 16) * 32;
+        for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) __stcg(mine + idx, block_sum(idx >> 5, idx & 31));
+        bar_sync(1, kDqThreads);
+        const int i_first = cta_of_chunk(p, rb * Cn);
+        const int i_last = cta_of_chunk(p, rb * Cn + Cn - 1);
+        volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(smem + kHolderOff + 4);
+        if (threadIdx.x == 0) {
+          unsigned old;
+          asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.ws_counter + i_first) : "memory");
+          const bool last = old == (unsigned)(i_last - i_first);
+          if (last) p.ws_counter[i_first] = 0u;  // self-resetting: ready for the next launch that uses this pool
+          *flag = last ? 1u : 0u;
+        }
+        bar_sync(1, kDqThreads);
+        if (*flag) {
+          for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) {
+            float total = 0.f;
+            for (int i = i_first; i <= i_last; ++i) {
+              int b0, e0;
+              cta_range(p, i, b0, e0);
+              const int sl = (b0 / Cn == rb) ? 0 : 1;
+              total += __ldcg(p.ws_partial + ((size_t)(i * 2 + sl) * 16) * 32 + idx);
+            }
+            emit(idx >> 5, idx & 31, total);
+          }
+        }
+        bar_sync(1, kDqThreads);  // the flag word is reused by the next partial segment
+      }
+      if (threadIdx.x == 0 && first_seg) TC_TRACE(13);
+      first_seg = false;
+      c += len;
+      ++rb;
+      cin = 0;
+    }
+    if (threadIdx.x == 0) TC_TRACE(14);
+  } else if (warp == kDqWarps) {
+    // =============================================================== TMA producer: the rest of the stream
+    while (pit.valid(c_end)) {
+      const int s = (int)(pseq % kWStages);
+      wait_all(sbase + bar_off(B_WEMPTY + s), ((pseq / kWStages) - 1u) & 1u);
+      produce();
+    }
+  } else {
+    // =============================================================== MMA issuer (one warp, one elected lane)
+    const uint32_t leader = elect_one();
+    constexpr uint32_t fmt = DT == TG_BF16 ? 1u : 0u;
+    constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(C::N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t step = x_single ? 256u : 2u * x_g8 * x_pitch;
+    const uint32_t lbo = x_single ? 64u : x_g8 * x_pitch;
+    const uint32_t sbo = x_pitch;
+    const uint32_t desc_hi = (sbo >> 4) | (1u << 14);  // descriptor version 1 (sm_100), no swizzle
+    uint32_t gst = 0, dseq = 0;
+    bar_sync(2, kDqThreads + 32);  // stage 0's activations are staged
+    int c = c_begin, cin = c_begin - rb_first * Cn;
+    while (c < c_end) {
+      const int len = min(Cn - cin, c_end - c);
+      const int nst = (len + 7) >> 3;
+      const int buf = (int)(dseq % C::NB);
+      if (dseq >= (uint32_t)C::NB) {
+        wait_all(sbase + bar_off(B_DEMPTY + buf), ((dseq / C::NB) - 1u) & 1u);
+        tc_fence_after();
+      }
+      const uint32_t dcol = tmem + (uint32_t)(buf * C::N);
+      uint32_t acc = 0;
+      for (int st = 0; st < nst; ++st, ++gst) {
+        const uint32_t xb = x0 + (gst % C::NX) * C::kXStageBytes;
+#pragma unroll
+        for (int Q = 0; Q < 2; ++Q) {
+          const uint32_t use = 2u * gst + (uint32_t)Q;
+          const int slot = (int)(use % C::NS);
+          wait_all(sbase + bar_off(B_AFULL + slot), (use / C::NS) & 1u);
+          tc_fence_after();
+          if (gst < 3 && Q == 0 && lane == 0) TC_TRACE(37 + gst * 3);
+          __syncwarp();
+          const uint32_t acol = tmem + (uint32_t)(C::kABase + slot * 64);
+          if (leader) {
+            // every tcgen05 issue of the warp sits in this one block: ptxas keeps it a real branch (a lone
+            // leader-predicated commit gets if-converted into a predicated R2UR + unpredicated UTCBAR, which
+            // faults when the warp is not converged)
+#pragma unroll
+            for (int T = 0; T < 8; ++T) {
+              const uint32_t addr = xb + (uint32_t)(Q * 8 + T) * step;
+              const uint64_t desc = ((uint64_t)desc_hi << 32) | (uint64_t)(((addr >> 4) & 0x3fffu) | ((lbo >> 4) << 16));
+              tc_mma(dcol, acol + (uint32_t)(T * 8), desc, idesc, acc);
+              acc = 1u;
+            }
+            tc_commit(sbase + bar_off(B_AEMPTY + slot));
+            if (Q == 1 && st == nst - 1) tc_commit(sbase + bar_off(B_DFULL + buf));  // the row block's sums are complete
+          }
+          acc = 1u;
+          __syncwarp();
+        }
+        if (gst < 3 && lane == 0) TC_TRACE(38 + gst * 3);
+      }
+      ++dseq;
+      c += len;
+      cin = 0;
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+#ifdef TG_W4_TRACE
+  if (threadIdx.x == 0) {
+    TC_TRACE(48);
+    if (p.trace != nullptr) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.trace[(size_t)blockIdx.x * 64 + 63] = smid;
+    }
+  }
+#endif
+  if (warp == kDqWarps + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  }
+}
+
+template <tg_dtype DT, int IK, int MB>
+__global__ void __launch_bounds__(Cfg<MB>::kThreads, Cfg<MB>::kMinBlocks) gemv_w4_tc_kernel(const ParamsTC p) {
+  gemv_w4_tc_body<DT, IK, MB, false>(p, Peers{});
+}
+// row-sharded variant: the epilogue stores into every rank's symmetric output buffer
+template <tg_dtype DT, int IK, int MB>
+__global__ void __launch_bounds__(Cfg<MB>::kThreads, Cfg<MB>::kMinBlocks) gemv_w4_tc_peer_kernel(const ParamsTC p,
+                                                                                               const __grid_constant__ Peers peers) {
+  gemv_w4_tc_body<DT, IK, MB, true>(p, peers);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+int g_ctas_per_sm = 0;  // 0 = heuristic (tuning: env TG_TC_CTAS)
+int g_split = -1;       // -1 = heuristic, 0 = whole row blocks per CTA, 1 = stream-K chunks (tuning: env TG_TC_SPLIT)
+
+struct DeviceInfo {
+  int n_sm = 0;
+  float* ws_partial = nullptr;
+  unsigned* ws_counter = nullptr;
+};
+static int device_info(DeviceInfo** out) {
+  static thread_local DeviceInfo info[kMaxDevices];
+  DeviceInfo& d = info[current_device_slot()];
+  if (d.n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (cudaGetSymbolAddress((void**)&d.ws_partial, g_ws_partial) != cudaSuccess ||
+        cudaGetSymbolAddress((void**)&d.ws_counter, g_ws_counter) != cudaSuccess) {
+      set_error("cudaGetSymbolAddress failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return TG_ERR_CUDA;
+    }
+    d.n_sm = n;
+    static bool env_read = false;
+    if (!env_read) {
+      if (getenv("TG_TC_CTAS")) g_ctas_per_sm = atoi(getenv("TG_TC_CTAS"));
+      if (getenv("TG_TC_SPLIT")) g_split = atoi(getenv("TG_TC_SPLIT"));
+      env_read = true;
+    }
+  }
+  *out = &d;
+  return TG_OK;
+}
+
+template <tg_dtype DT, int IK, int MB>
+int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) {
+  using C = Cfg<MB>;
+  auto kern = gemv_w4_tc_kernel<DT, IK, MB>;
+  auto kern_peer = gemv_w4_tc_peer_kernel<DT, IK, MB>;
+  static thread_local bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
+  if (!attr_set) {
+    for (const void* f : {(const void*)kern, (const void*)kern_peer}) {
+      if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem) != cudaSuccess ||
+          cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) !=
+              cudaSuccess) {
+        set_error("cudaFuncSetAttribute(smem=%u) failed: %s", C::kSmem, cudaGetErrorString(cudaGetLastError()));
+        return TG_ERR_CUDA;
+      }
+    }
+    attr_set = true;
+  }
+  DeviceInfo* di = nullptr;
+  int rc = device_info(&di);
+  if (rc != TG_OK) return rc;
+
+  // Work split.  One CTA per SM while a CTA's share is small (the second slot of every SM is then free for the next
+  // kernel of the stream, whose prologue overlaps our dequant), two per SM for the long ones (they hide each other's
+  // row-block boundaries).  Stream-K over 128-k chunks when that shortens the longest CTA by more than the fix-up
+  // of a shared row block costs (~kFixup chunks), else whole row blocks per CTA.
+  const int Cn = p.chunks_per_row;
+  const int64_t chunks = (int64_t)row_blocks * Cn;
+  int per_sm = g_ctas_per_sm;
+  if (per_sm <= 0) per_sm = (chunks >= (int64_t)di->n_sm * 2 * 40) ? 2 : 1;
+  if (per_sm > C::kMinBlocks) per_sm = C::kMinBlocks;
+  int64_t slots = (int64_t)di->n_sm * per_sm;
+  if (slots > kMaxGrid) slots = kMaxGrid;
+  constexpr int64_t kFixup = 6;
+  const int64_t g_split_ctas = chunks < slots ? chunks : slots;
+  const int64_t g_whole_ctas = row_blocks < slots ? row_blocks : slots;
+  const int64_t t_split = div_up(chunks, g_split_ctas) + kFixup;
+  const int64_t t_whole = div_up(row_blocks, g_whole_ctas) * Cn;
+  const bool split = g_split >= 0 ? g_split != 0 : t_split < t_whole;
+  int64_t G;
+  if (split) {
+    G = g_split_ctas;
+    p.ug = 1;
+    p.cq = (int)(chunks / G);
+    p.cr = (int)(chunks % G);
+  } else {
+    G = g_whole_ctas;
+    p.ug = Cn;
+    p.cq = (int)(row_blocks / G);
+    p.cr = (int)(row_blocks % G);
+  }
+  static std::atomic<unsigned> pool{0};
+  const unsigned pl = pool.fetch_add(1u, std::memory_order_relaxed) % kWsPools;
+  p.ws_partial = di->ws_partial + (size_t)pl * (kMaxGrid * 2 * 16 * 32);
+  p.ws_counter = di->ws_counter + (size_t)pl * kMaxGrid;
+
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)G, 1, 1);
+  cfg.blockDim = dim3(C::kThreads, 1, 1);
+  cfg.dynamicSmemBytes = C::kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  int na = 0;
+  if (g_pdl) {
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  cudaError_t e = peers.n > 0 ? cudaLaunchKernelEx(&cfg, kern_peer, p, peers) : cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) {
+    set_error("gemv_w4_tc launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return TG_ERR_CUDA;
+  }
+  count_launch();
+  return TG_OK;
+}
+
+template <tg_dtype DT, int IK>
+int launch_m(ParamsTC p, const Peers& peers0, int row_blocks, int64_t rows_x, const uint16_t* x, uint16_t* y, cudaStream_t st) {
+  Peers peers = peers0;
+  for (int64_t r0 = 0; r0 < rows_x; r0 += 16) {  // one pass carries up to 16 activation rows
+    p.m = (int)((rows_x - r0) < 16 ? (rows_x - r0) : 16);
+    p.x = x + r0 * p.k;
+    p.y = y + r0 * p.y_stride;
+    for (int r = 0; r < peers0.n; ++r) peers.y[r] = peers0.y[r] + r0 * p.y_stride;
+    int rc;
+    if (p.m <= 4) rc = launch_one<DT, IK, 4>(p, peers, row_blocks, st);
+    else if (p.m <= 8) rc = launch_one<DT, IK, 8>(p, peers, row_blocks, st);
+    else rc = launch_one<DT, IK, 16>(p, peers, row_blocks, st);
+    if (rc != TG_OK) return rc;
+  }
+  return TG_OK;
+}
+
+template <tg_dtype DT>
+int launch_ik(const ParamsTC& p, const Peers& peers, int ik, int row_blocks, int64_t rows_x, const uint16_t* x, uint16_t* y,
+              cudaStream_t st) {
+  switch (ik) {
+    case 2: return launch_m<DT, 2>(p, peers, row_blocks, rows_x, x, y, st);
+    case 4: return launch_m<DT, 4>(p, peers, row_blocks, rows_x, x, y, st);
+    case 8: return launch_m<DT, 8>(p, peers, row_blocks, rows_x, x, y, st);
+  }
+  set_error("B-layout int4 innerKTiles must be 2, 4 or 8 (got %d)", ik);
+  return TG_ERR_INVALID_ARGUMENT;
+}
+
+}  // namespace tc
+
+int launch_gemm_w4_tc_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut, const uint8_t* exps,
+                        int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik, tg_w4_format fmt, tg_dtype dt,
+                        const uint16_t* const_lut, cudaStream_t st, void* const* y_peers, int n_peers, int64_t y_row_stride,
+                        int silu_pairs) {
+  tc::ParamsTC p{};
+  w4::Peers peers{};
+  peers.n = n_peers;
+  for (int r = 0; r < n_peers; ++r) peers.y[r] = static_cast<uint16_t*>(y_peers[r]);
+  p.w = reinterpret_cast<const uint8_t*>(w);
+  p.sz = (fmt == TG_W4_MX4) ? nullptr : reinterpret_cast<const uint32_t*>(sz);
+  p.exps = (fmt == TG_W4_MX4) ? exps : nullptr;
+  p.w_rows = (int)w_rows;
+  p.k = (int)k;
+  p.glog2 = group == 32 ? 5 : group == 64 ? 6 : group == 128 ? 7 : 8;
+  p.tile_stride = 4 * k;
+  p.y_stride = n_peers > 0 ? y_row_stride : silu_pairs ? w_rows / 2 : w_rows;
+  if (fmt == TG_W4_ANY4_GLOBAL || fmt == TG_W4_ANY4_ROWWISE) {
+    p.lut = reinterpret_cast<const uint16_t*>(lut);
+    p.lut_stride = (fmt == TG_W4_ANY4_ROWWISE) ? 16 : 0;
+  } else {
+    p.lut = const_lut;  // int4 / mx4: constant table, same for every row
+    p.lut_stride = 0;
+  }
+  p.chunks_per_row = (int)div_up(k, 128);
+  const int64_t row_blocks = div_up(w_rows, 32);
+  if (row_blocks * p.chunks_per_row >= (1ll << 31)) {
+    set_error("w_rows * k = %lld * %lld exceeds the 2^43 elements one launch can index", (long long)w_rows, (long long)k);
+    return TG_ERR_UNSUPPORTED;
+  }
+  p.flags = (w4::g_static_weights ? 8 : 0) | (silu_pairs ? 16 : 0);
+#ifdef TG_W4_TRACE
+  p.trace = w4::g_trace_buf;
+#endif
+  if (dt == TG_BF16)
+    return tc::launch_ik<TG_BF16>(p, peers, ik, (int)row_blocks, rows_x, (const uint16_t*)x, (uint16_t*)y, st);
+  return tc::launch_ik<TG_FP16>(p, peers, ik, (int)row_blocks, rows_x, (const uint16_t*)x, (uint16_t*)y, st);
+}
+
+void set_tc_ctas_per_sm(int v) { tc::g_ctas_per_sm = v; }
+
+}  // namespace tg
