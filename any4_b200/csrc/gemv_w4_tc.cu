@@ -10,27 +10,29 @@
 //    every dequant warp owns row row_of_lane(L).  The row's 16-entry LUT is expanded once per row block into a
 //    256-entry byte-PAIR table  pair[b] = (LUT[b & 15], LUT[b >> 4])  stored bank-private in shared memory
 //    (entry e of lane L at e*256 + 4L), so both nibbles of a packed byte are dequantised by ONE conflict-free
-//    LDS.32 whose address is ONE PRMT.  Group scale/zero: one fma.rn.{bf16,f16}x2 per pair - the same single-rounded
-//    FMA as the reference (MatrixLayoutB.cuh:1042-1046), hence bit-identical dequantised weights.
-//  * The dequantised bf16/fp16 pairs never touch shared memory or mma.sync registers: each thread writes its row's
-//    k-slice straight into TENSOR MEMORY with tcgen05.st (32x32b: thread = TMEM lane = weight row, 8 columns = one
-//    K = 16 step), and ONE elected thread issues tcgen05.mma (M = 128, N = 4 * MB, K = 16, kind::f16, fp32
-//    accumulators in TMEM) with A read from TMEM and the activations read from shared memory through a K-major
-//    no-swizzle descriptor.  The four warps of a "quad" own the four 32-lane TMEM sub-partitions; all four work on
-//    the SAME 32 weight rows but on different 128-wide k chunks, and the activation operand is block structured:
+//    LDS.32 whose address is ONE PRMT (the table base is an immediate).  Group scale/zero: one
+//    fma.rn.{bf16,f16}x2 per pair - the same single-rounded FMA as the reference (MatrixLayoutB.cuh:1042-1046),
+//    hence bit-identical dequantised weights.
+//  * The dequantised pairs never touch shared memory or mma.sync registers: each thread writes its row's k-slice
+//    straight into TENSOR MEMORY with tcgen05.st (32x32b: thread = TMEM lane = weight row, 8 columns = one K = 16
+//    step), and ONE elected thread issues tcgen05.mma (M = 128, N = 4 * MB, K = 16, kind::f16, fp32 accumulators
+//    in TMEM) with A read from TMEM and the activations read from shared memory through a K-major no-swizzle
+//    descriptor.  The four warps of a "quad" own the four 32-lane TMEM sub-partitions; all of them work on the
+//    SAME 32 weight rows but on different 128-wide k chunks, and the activation operand is block structured:
 //    operand column 4*mi + j carries activation row mi for the k chunk of quarter j, so accumulator element
-//    (lane 32j + L, column 4*mi + j) is the partial dot product of lane L's row over quarter j's chunk.  The other
+//    (lane 32j + L, column 4*mi + j) is the partial dot product of lane L's row over quarter j's chunks.  The other
 //    columns of a lane hold cross terms nobody reads.  One pass therefore handles 16 activation rows (N = 64).
 //  * Weights stream HBM -> shared memory with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx, 4 KiB copies,
-//    L2 evict-first) into a 3 x 16 KiB ring fed by a producer thread.  The activations are staged per ring stage by
-//    dedicated warps (global -> PRMT k-permutation -> the operand layout the descriptor describes); nothing about k
-//    or m has to fit shared memory, so any k works.
-//  * Work decomposition is stream-K over (row block, 128-k chunk) units: CTA i of G processes the contiguous unit
-//    range [i*U/G, (i+1)*U/G).  A row block cut by a range boundary is finished by the LAST of its CTAs to arrive
-//    (fp32 partials in a device workspace, arrival counter, summed in CTA order: deterministic).
-//  * The CTA needs 113 KB of shared memory, 256 TMEM columns and <= 80 registers x 384 threads, so TWO CTAs - of the
-//    same GEMV or of two consecutive GEMVs of a stream (programmatic dependent launch) - share an SM: the prologue,
-//    first-byte latency and row-block boundaries of one hide under the dequant of the other.  With
+//    L2 evict-first) into a 3 x 16 KiB ring fed by a producer warp.  The activations are staged by the dequant
+//    threads themselves (global -> PRMT k-permutation -> the operand layout the descriptor describes): for one
+//    activation row the whole x stays resident (k <= 14336), otherwise it is staged per ring stage, so any k works.
+//  * Work units are ring stages (32 rows x 1024 k).  CTA i of G processes a contiguous range of the (row block,
+//    stage) sequence (stream-K) or whole row blocks, whichever finishes earlier.  A row block cut by a range
+//    boundary is finished by the LAST of its CTAs to arrive (fp32 partials in a device workspace, arrival counter,
+//    summed in CTA order: deterministic).
+//  * The decode CTA needs 113 KB of shared memory, 256 TMEM columns and 96 registers x 320 threads, so TWO CTAs - of
+//    the same GEMV or of two consecutive GEMVs of a stream (programmatic dependent launch) - share an SM: the
+//    prologue, first-byte latency and row-block boundaries of one hide under the dequant of the other.  With
 //    TG_OPT_STATIC_WEIGHTS the weight stream, the table build and the dequant of the first TMEM slots start before
 //    the previous kernel has finished; only the activation staging (and with it every MMA and store) waits.
 //
@@ -58,10 +60,11 @@ constexpr uint32_t kWRingOff = kRegionA;
 constexpr uint32_t kXDenseOff = kWRingOff + kWStages * kWStageStride;  // activation ring of the MB >= 8 kernels
 constexpr uint32_t kSmemBase = 0x400;       // shared-window address of the dynamic shared memory (no static smem): see lds_table
 constexpr int kCtrlHl = 240;                // odd half-lines 240.. hold the mbarriers and the TMEM base address
+constexpr int kXResMaxStages = 14;          // resident activations: 16 half-lines per 1024 k -> k <= 14336
 constexpr int kMaxGrid = 512;
 constexpr int kWsPools = 4;
 
-// split fix-up workspace (see finish_partial): fp32 partial sums [pool][CTA][slot 0/1][mi][row] and arrival counters
+// split fix-up workspace: fp32 partial sums [pool][CTA][slot 0/1][mi][row] and arrival counters
 __device__ float g_ws_partial[kWsPools][kMaxGrid * 2 * 16 * 32];
 __device__ unsigned g_ws_counter[kWsPools][kMaxGrid];
 
@@ -69,7 +72,7 @@ struct ParamsTC {
   const uint8_t* w;      // packed weight
   const uint16_t* x;     // [m][k]
   uint16_t* y;           // [m][y_stride]
-  const uint32_t* sz;    // [k/g][w_rows] (scale, zero) pairs, null for mx4
+  const uint32_t* sz;    // [k/g][w_rows] (scale, zero) pairs (unused for mx4)
   const uint8_t* exps;   // [w_rows][k/g] e8m0, mx4 only
   const uint16_t* lut;   // [16] or [w_rows][16]
   float* ws_partial;     // this launch's workspace pool
@@ -82,8 +85,9 @@ struct ParamsTC {
   int k;
   int glog2;             // log2(group)
   int chunks_per_row;    // C = ceil(k / 128)
-  int ug;                // chunks per work unit: 1 (stream-K over chunks) or C (whole row blocks per CTA)
-  int cq, cr;            // units per CTA: U / G and U % G
+  int stages_per_row;    // S = ceil(C / 8): work units per row block
+  int ug;                // stages per scheduling unit: 1 (stream-K over stages) or S (whole row blocks per CTA)
+  int cq, cr;            // scheduling units per CTA: U / G and U % G
   int flags;             // bit 3: static weights; bit 4: silu(gate)*up over interleaved row pairs
 #ifdef TG_W4_TRACE
   unsigned long long* trace;  // [CTAs][64] globaltimer stamps (scripts/trace_tc.py)
@@ -149,33 +153,41 @@ __device__ __forceinline__ uint32_t bar_off(int i) { return odd_hl(kCtrlHl + (i 
 enum : int { B_WFULL = 0, B_WEMPTY = 3, B_AFULL = 6, B_AEMPTY = 9, B_DFULL = 12, B_DEMPTY = 14, B_COUNT = 16 };
 constexpr uint32_t kHolderOff = 242u * 256u + 128u;  // TMEM base address; +4: "this CTA is the last arriver" flag
 
-template <int MB>
+template <int MB, bool XRES>
 struct Cfg {
+  static_assert(!XRES || MB == 4, "resident activations: decode kernel only");
   static constexpr int N = 4 * MB;                 // MMA N: operand column 4*mi + j
   static constexpr int NS = 3;                     // TMEM A slots (64 columns = one 128-k chunk per quarter), shared by the quads
   static constexpr int NB = MB == 16 ? 1 : 2;      // accumulator buffers
-  static constexpr int NX = 3;                     // activation ring depth
-  static constexpr int NIT = MB == 4 ? 4 : MB;     // 8-byte activation pieces a dequant thread stages per ring stage (max)
+  static constexpr int NX = 3;                     // activation ring depth (streamed activations)
   static constexpr int XR = MB == 4 ? 8 : 2 * MB;  // register ring of pieces in flight: XR / pieces-per-stage stages ahead
   static constexpr int kWarps = 10;                // 8 dequant, TMA producer, MMA issuer
   static constexpr int kThreads = kWarps * 32;
   static constexpr int kABase = NB * N;            // TMEM: accumulators first, then the A slots
-  static constexpr int kRedHl0 = MB == 4 ? 192 : 0;  // reduction scratch [4][MB] half-lines
+  static constexpr int kRedHl0 = XRES ? 224 : (MB == 4 ? 192 : 0);  // reduction scratch [4][MB] half-lines
   static constexpr uint32_t kXStageBytes = MB == 4 ? 64u * 256u : 32u * (MB / 2) * 128u;
   static constexpr uint32_t kSmem = MB == 4 ? kXDenseOff : kXDenseOff + NX * kXStageBytes;
   static constexpr int kMinBlocks = MB == 4 ? 2 : 1;
 };
-static_assert(Cfg<4>::kSmem <= 115712u, "two CTAs of the decode kernel must fit one SM");
-static_assert(Cfg<16>::kSmem <= 232448u, "exceeds the 227 KiB opt-in shared memory of sm_100");
-static_assert(Cfg<16>::kABase + 3 * 64 <= 256 && Cfg<8>::kABase + 3 * 64 <= 256, "TMEM budget");
+static_assert(Cfg<4, true>::kSmem <= 115712u, "two CTAs of the decode kernel must fit one SM");
+static_assert(Cfg<16, false>::kSmem <= 232448u, "exceeds the 227 KiB opt-in shared memory of sm_100");
+static_assert(Cfg<16, false>::kABase + 3 * 64 <= 256 && Cfg<8, false>::kABase + 3 * 64 <= 256, "TMEM budget");
 
 // ---- small PTX wrappers ----
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// A try_wait costs ~200 cycles even on a completed phase (scripts/microbench/tc_probe2.cu), so every lane waits
-// itself (no poll-then-confirm) and the kernel is organised around as few waits per ring stage as possible.
-__device__ __forceinline__ void wait_all(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+// non-blocking probe (acquire).  A probe costs ~200 cycles of latency even on a completed phase
+// (scripts/microbench/tc_probe2.cu), so the dequant loop probes the NEXT stage's barriers while it still has a stage
+// of lookups to issue and only falls back to the blocking wait when the probe said "not yet".
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return ok;
+}
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -222,38 +234,37 @@ __device__ __forceinline__ void store_out(uint16_t* y, const Peers& peers, int64
   }
 }
 
-// CTA i of the grid owns units [begin, end) (in 128-k chunks): the first cr CTAs get cq + 1 units of ug chunks
+// CTA i of the grid owns stage units [begin, end): the first cr CTAs get cq + 1 scheduling units of ug stages
 __device__ __forceinline__ void cta_range(const ParamsTC& p, int i, int& begin, int& end) {
   begin = (i * p.cq + min(i, p.cr)) * p.ug;
   end = begin + (p.cq + (i < p.cr ? 1 : 0)) * p.ug;
 }
-__device__ __forceinline__ int cta_of_chunk(const ParamsTC& p, int u) {  // split mode only (ug == 1)
+__device__ __forceinline__ int cta_of_unit(const ParamsTC& p, int u) {  // split mode only (ug == 1)
   const int big = p.cr * (p.cq + 1);
   return u < big ? u / (p.cq + 1) : p.cr + (u - big) / p.cq;
 }
 
-// Cursor over the CTA's ring stages: segments (one per row block touched), 8 chunks per stage.
-struct StageIt {
-  int c, cin, len, st, rb;
-  __device__ __forceinline__ void init(int c_begin, int c_end, int Cn) {
-    c = c_begin;
-    rb = c_begin / Cn;
-    cin = c_begin - rb * Cn;
-    len = min(Cn - cin, c_end - c);
-    st = 0;
+// Cursor over the CTA's (row block, stage-in-row) sequence
+struct Cursor {
+  int u, rb, sir;
+  __device__ __forceinline__ void init(int u0, int S) {
+    u = u0;
+    rb = u0 / S;
+    sir = u0 - rb * S;
   }
-  __device__ __forceinline__ bool valid(int c_end) const { return c < c_end; }
-  __device__ __forceinline__ int cs() const { return cin + st * 8; }   // first chunk (within the row) of the stage
-  __device__ __forceinline__ int rem() const { return len - st * 8; }  // chunks left in the segment (stage: min(8, rem))
-  __device__ __forceinline__ void next(int c_end, int Cn) {
-    if ((st + 1) * 8 < len) {
-      ++st;
-    } else {
-      c += len;
-      cin = 0;
-      st = 0;
+  __device__ __forceinline__ void next(int S) {
+    ++u;
+    if (++sir == S) {
+      sir = 0;
       ++rb;
-      len = min(Cn, c_end - c);
+    }
+  }
+  __device__ __forceinline__ void skip(int n, int S) {  // n <= S - sir
+    u += n;
+    sir += n;
+    if (sir == S) {
+      sir = 0;
+      ++rb;
     }
   }
 };
@@ -264,14 +275,14 @@ struct StageIt {
 //               into TMEM lanes 32j.. of A slot (2 * stage + Q) % 3, and stages its share of the activations
 //   warp 8      bulk-TMA producer of the weight ring
 //   warp 9      MMA issuer (one elected lane): per stage and quad 8 x tcgen05.mma + commit
-// Ordering without extra barriers: a warp stores its pieces of stage i+1's activations BEFORE it signals its A slot
-// of stage i, and the issuer starts stage i+1 only after it has seen all eight A-slot signals of stage i; an A slot
-// is refilled only after the commit of its previous use, which (one issuer: commits are cumulative) also proves that
-// the MMAs of stage i-2 are done, i.e. that activation ring slot (i+1) % 3 is free.
+// Ordering without extra barriers (streamed activations): a warp stores its pieces of stage i+1's activations BEFORE
+// it signals its A slot of stage i, and the issuer starts stage i+1 only after it has seen all eight A-slot signals
+// of stage i; an A slot is refilled only after the commit of its previous use, which (one issuer: commits are
+// cumulative) also proves that the MMAs of stage i-2 are done, i.e. that activation ring slot (i+1) % 3 is free.
 // ---------------------------------------------------------------------------------------
-template <tg_dtype DT, int IK, int MB, bool PEERS>
+template <tg_dtype DT, int IK, int MB, bool XRES, bool MX4, bool PEERS>
 __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& peers) {
-  using C = Cfg<MB>;
+  using C = Cfg<MB, XRES>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int lane = threadIdx.x & 31;
@@ -287,18 +298,18 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
   if (sbase != kSmemBase) __trap();  // lds_table() relies on it
   if (!static_w) griddep_wait();
 
-  int c_begin, c_end;
-  cta_range(p, (int)blockIdx.x, c_begin, c_end);
+  int u_begin, u_end;
+  cta_range(p, (int)blockIdx.x, u_begin, u_end);
   const int Cn = p.chunks_per_row;
-  const int rb_first = c_begin / Cn;
+  const int S = p.stages_per_row;
   const int n_groups = p.k >> p.glog2;
-  const bool is_mx4 = p.sz == nullptr;
 
   // activation operand geometry.  K step s of a ring stage (s = Q*8 + T: quad Q, k-tile T of the chunk) reads operand
   // rows n = 4*mi + j (activation row mi, quarter j -> chunk Q*4 + j of the stage), 16 K values each:
   //   K index 2c + f  <->  k = 16*tile + c + 8f      (the order the packed bytes dequantise in)
   // 16-byte unit (s, h, n) = K indices 8h..8h+7.  Placement (the strides are what the descriptor is told):
-  //   MB = 4, m = 1 : s*256 + h*64 + j*16          in the odd half-lines of region A (rows 4.. alias the other half)
+  //   m = 1 (MB = 4): s*256 + h*64 + j*16           in the odd half-lines of region A (rows 4.. alias the other half);
+  //                   resident: stage t of the row at t*16*256, else ring slot * 16 KiB
   //   MB = 4, m >= 2: ((s*2 + h)*G8 + n/8)*256 + (n%8)*16,  G8 = 1 (m = 2) or 2
   //   MB >= 8       : ((s*2 + h)*G8 + n/8)*128 + (n%8)*16 in the dense ring, G8 = MB / 2
   const bool x_single = MB == 4 && p.m == 1;
@@ -307,27 +318,25 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
   const uint32_t x0 = sbase + (MB == 4 ? 128u : kXDenseOff);
 
   // ------------------------------------------------------------------ setup
-  StageIt pit;  // producer cursor (warp 8)
-  pit.init(c_begin, c_end, Cn);
+  Cursor pc;  // producer cursor (warp 8)
+  pc.init(u_begin, S);
   uint32_t pseq = 0;
   uint64_t pol = 0;
   // one ring stage: lane 0 arms the barrier, lanes 0..3 issue one 4 KiB n-tile copy each
   auto produce = [&]() {
     const int s = (int)(pseq % kWStages);
-    const int rb = pit.rb;
-    const int tiles_valid = min(32, p.w_rows - rb * 32) >> 3;
-    const int nvalid = min(8, pit.rem());
-    const int k0 = pit.cs() * 128;
-    const uint32_t bytes = (uint32_t)min(nvalid * 128, p.k - k0) * 4u;  // per n-tile: 8 rows * k / 2
+    const int tiles_valid = min(32, p.w_rows - pc.rb * 32) >> 3;
+    const int k0 = pc.sir * 1024;
+    const uint32_t bytes = (uint32_t)min(1024, p.k - k0) * 4u;  // per n-tile: 8 rows * k / 2
     const uint32_t bar = sbase + bar_off(B_WFULL + s);
     if (lane == 0) mbar_expect_tx(bar, bytes * (uint32_t)tiles_valid);
     __syncwarp();
     if (lane < tiles_valid)
       bulk_g2s(sbase + kWRingOff + (uint32_t)s * kWStageStride + tile_off<IK>(lane),
-               p.w + (int64_t)(rb * 4 + lane) * p.tile_stride + (int64_t)k0 * 4, bytes, bar, pol);
+               p.w + (int64_t)(pc.rb * 4 + lane) * p.tile_stride + (int64_t)k0 * 4, bytes, bar, pol);
     if (lane == 0 && pseq < 3) TC_TRACE(17 + pseq);
     ++pseq;
-    pit.next(c_end, Cn);
+    pc.next(S);
   };
   uint4 lut0 = make_uint4(0, 0, 0, 0), lut1 = lut0;
   uint32_t lut_hi[2] = {0u, 0u};
@@ -360,13 +369,13 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
     __syncwarp();
     // the weight stream starts right here: the ring has kWStages free stages, nobody has to be asked
     pol = l2_evict_first_policy();
-    for (int i = 0; i < kWStages && pit.valid(c_end); ++i) produce();
+    for (int i = 0; i < kWStages && pc.u < u_end; ++i) produce();
   } else if (warp == kDqWarps + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kHolderOff), "r"(256u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else {
-    load_lut(rb_first);  // in flight across the setup barrier
+    load_lut(u_begin / S);  // in flight across the setup barrier
   }
   tc_fence_before();
   __syncthreads();
@@ -380,26 +389,31 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
     const uint32_t lane4 = (uint32_t)lane * 4u;
     const uint32_t wl_off = kWRingOff + tile_off<IK>(rl >> 3) + (uint32_t)warp * 512u + (uint32_t)(rl & 7) * Geo<IK>::kRowStride;
     const uint32_t my_tmem = tmem + ((uint32_t)(j * 32) << 16);
-    uint32_t gst = 0;   // ring stage counter of the CTA (weight ring slot gst % 3, A slot use 2 * gst + Q)
     uint32_t dseq = 0;  // row blocks (accumulator buffer dseq % NB)
+    uint32_t gst = 0;   // ring stages done by this CTA
     bool first_seg = true;
+    // weight ring slot / phase of the current stage; A slot / phase of this quad's current use (= 2 * stage + Q)
+    uint32_t ws = 0, wpar = 0, as = (uint32_t)Q, apar = 0;
+    int free_uses = Q == 0 ? 2 : 1;     // uses 0, 1, 2 find their A slot untouched
+    uint32_t w_ready = 0, a_ready = 0;  // answers of the probes issued one stage ago
 
     // Small global loads issued while the weight ring is full come back only after everything queued in front of
-    // them (~2 us for 96 KB per SM), so the per-stage operands - group (scale, zero) words and activation pieces -
-    // travel through REGISTER RINGS filled several stages ahead: a stage consumes the head, shifts, and requests
-    // the stage `depth` ahead at the tail.  Depth = ring size / values per stage (switch on the runtime count).
+    // them (~2 us for 96 KB per SM), so the per-stage operands - group (scale, zero) words and streamed activation
+    // pieces - travel through REGISTER RINGS filled several stages ahead: a stage consumes the head, shifts, and
+    // requests the stage `depth` ahead at the tail.  Depth = ring size / values per stage.
 
     // ---- group words: nsz per stage (1: group >= 128, 2: group 64, 4: group 32), ring of 8 -> 8 / 4 / 2 stages ----
     const int nsz = p.glog2 >= 7 ? 1 : (p.glog2 == 6 ? 2 : 4);
     uint32_t szr[8];
-    StageIt zl;
-    zl.init(c_begin, c_end, Cn);
-    auto sz_word = [&](int t, int n) -> uint32_t {  // word t of n for this warp's chunk of stage zl
-      if (!zl.valid(c_end) || warp >= zl.rem()) return 0u;
-      const int row = min(zl.rb * 32 + rl, p.w_rows - 1);
-      const int gi = min(((zl.cs() + warp) * 128 + t * (128 / n)) >> p.glog2, n_groups - 1);
-      return is_mx4 ? (e8m0_to_dt<DT>((uint32_t)p.exps[(int64_t)row * n_groups + gi]) | 0x80000000u)  // zero = -0
-                    : p.sz[(int64_t)gi * p.w_rows + row];
+    Cursor zc;
+    zc.init(u_begin, S);
+    auto sz_word = [&](int t, int n) -> uint32_t {  // word t of n for this warp's chunk of stage zc
+      const int cc = zc.sir * 8 + warp;
+      if (zc.u >= u_end || cc >= Cn) return 0u;
+      const int row = min(zc.rb * 32 + rl, p.w_rows - 1);
+      const int gi = min((cc * 128 + t * (128 / n)) >> p.glog2, n_groups - 1);
+      if constexpr (MX4) return e8m0_to_dt<DT>((uint32_t)p.exps[(int64_t)row * n_groups + gi]) | 0x80000000u;  // zero = -0
+      else return p.sz[(int64_t)gi * p.w_rows + row];
     };
     auto sz_fill = [&](auto n_) {  // prologue: the first 8 / n stages
       constexpr int n = decltype(n_)::value;
@@ -407,7 +421,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       for (int d = 0; d < 8 / n; ++d) {
 #pragma unroll
         for (int t = 0; t < n; ++t) szr[d * n + t] = sz_word(t, n);
-        zl.next(c_end, Cn);
+        zc.next(S);
       }
     };
     // consume this stage's words into (s, s) / (z, z) pairs for the four 32-k quarters, shift, request the tail stage
@@ -423,72 +437,79 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       for (int i = 0; i + n < 8; ++i) szr[i] = szr[i + n];
 #pragma unroll
       for (int t = 0; t < n; ++t) szr[8 - n + t] = sz_word(t, n);
-      zl.next(c_end, Cn);
-    };
-
-    // ---- activation staging: thread (warp w, lane) owns the 8-byte pieces f of the units (s = 2w + slo, h, n) ----
-    // lane = f | j<<1 | (h or mi&1)<<3 | slo<<4: a half-warp writes one contiguous 128-byte half-line (conflict free)
-    // and reads whole 32-byte sectors of x.  Pieces per stage: 1 (m = 1), 2 (m = 2), 4 (m = 3, 4), MB (MB >= 8).
-    StageIt xl, xs;
-    xl.init(c_begin, c_end, Cn);
-    xs = xl;
-    uint32_t xs_seq = 0;
-    uint2 xr[C::XR];
-    const int x_f = lane & 1, x_j = (lane >> 1) & 3, x_b3 = (lane >> 3) & 1, x_s = 2 * warp + (lane >> 4);
-    const int x_ch = (x_s >> 3) * 4 + x_j;                     // chunk of the stage
-    const int x_koff = x_ch * 128 + (x_s & 7) * 16 + 8 * x_f;  // + 4h
-    const int x_nit = x_single ? 1 : 2 * (int)x_g8;
-    auto x_piece = [&](int it) -> uint2 {  // piece `it` of stage xl
-      const int h = x_single ? x_b3 : (it & 1);
-      const int mi = x_single ? 0 : (it >> 1) * 2 + x_b3;
-      const int kk = xl.cs() * 128 + x_koff + 4 * h;
-      if (xl.valid(c_end) && x_ch < xl.rem() && kk < p.k && mi < p.m)
-        return *reinterpret_cast<const uint2*>(p.x + (int64_t)mi * p.k + kk);
-      return make_uint2(0u, 0u);
-    };
-    auto x_fill = [&](auto n_) {
-      constexpr int n = decltype(n_)::value;
-#pragma unroll
-      for (int d = 0; d < C::XR / n; ++d) {
-#pragma unroll
-        for (int it = 0; it < n; ++it) xr[d * n + it] = x_piece(it);
-        xl.next(c_end, Cn);
-      }
-    };
-    // store the head stage's pieces into activation ring slot xs_seq % NX, shift, request the tail stage
-    auto x_step = [&](auto n_) {
-      constexpr int n = decltype(n_)::value;
-      if (xs.valid(c_end)) {
-        const uint32_t xb = x0 + (xs_seq % C::NX) * C::kXStageBytes;
-#pragma unroll
-        for (int it = 0; it < n; ++it) {
-          // lane f = 0 holds x[k0 + 4h ..+3], lane f = 1 holds x[k0 + 8 + 4h ..+3]; unit = (lo0,hi0,lo1,hi1,lo2,hi2,lo3,hi3):
-          // lane 0 writes the first 8 bytes (needs the partner's .x), lane 1 the last 8 (needs the partner's .y)
-          const uint32_t got = __shfl_xor_sync(0xffffffffu, x_f ? xr[it].x : xr[it].y, 1);
-          const uint32_t a = x_f ? got : xr[it].x, b = x_f ? xr[it].y : got;
-          uint32_t dst;
-          if (x_single) {
-            dst = xb + (uint32_t)x_s * 256u + (uint32_t)x_b3 * 64u + (uint32_t)x_j * 16u + (uint32_t)x_f * 8u;
-          } else {
-            const uint32_t h = it & 1, grp = it >> 1;
-            dst = xb + ((uint32_t)(x_s * 2 + h) * x_g8 + grp) * x_pitch + (uint32_t)(x_b3 * 4 + x_j) * 16u + (uint32_t)x_f * 8u;
-          }
-          sts64(dst, prmt(a, b, 0x5410u), prmt(a, b, 0x7632u));
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
-        ++xs_seq;
-        xs.next(c_end, Cn);
-      }
-#pragma unroll
-      for (int i = 0; i + n < C::XR; ++i) xr[i] = xr[i + n];
-#pragma unroll
-      for (int it = 0; it < n; ++it) xr[C::XR - n + it] = x_piece(it);
-      xl.next(c_end, Cn);
+      zc.next(S);
     };
     using I1 = std::integral_constant<int, 1>;
     using I2 = std::integral_constant<int, 2>;
     using I4 = std::integral_constant<int, 4>;
     using IM = std::integral_constant<int, MB>;
+
+    // ---- activation staging: thread (warp w, lane) owns the 8-byte pieces f of the units (s = 2w + slo, h, n) ----
+    // lane = f | j<<1 | (h or mi&1)<<3 | slo<<4: a half-warp writes one contiguous 128-byte half-line (conflict free)
+    // and reads whole 32-byte sectors of x.  Pieces per stage: 1 (m = 1), 2 (m = 2), 4 (m = 3, 4), MB (MB >= 8).
+    const int x_f = lane & 1, x_j = (lane >> 1) & 3, x_b3 = (lane >> 3) & 1, x_s = 2 * warp + (lane >> 4);
+    const int x_ch = (x_s >> 3) * 4 + x_j;                     // chunk of the stage
+    const int x_koff = x_ch * 128 + (x_s & 7) * 16 + 8 * x_f;  // + 4h
+    // the pair (lane f = 0: x[k0 + 4h ..+3], lane f = 1: x[k0 + 8 + 4h ..+3]) becomes the 16-byte unit
+    // (lo0,hi0,lo1,hi1,lo2,hi2,lo3,hi3): lane 0 writes its first 8 bytes (needs the partner's .x), lane 1 the rest
+    auto x_put = [&](uint32_t dst, uint2 v) {
+      const uint32_t got = __shfl_xor_sync(0xffffffffu, x_f ? v.x : v.y, 1);
+      const uint32_t a = x_f ? got : v.x, b = x_f ? v.y : got;
+      sts64(dst + (uint32_t)x_f * 8u, prmt(a, b, 0x5410u), prmt(a, b, 0x7632u));
+    };
+    // streamed activations
+    Cursor xl, xs;
+    xl.init(u_begin, S);
+    xs = xl;
+    uint32_t xs_seq = 0;
+    uint2 xr[XRES ? 1 : C::XR];
+    const int x_nit = x_single ? 1 : 2 * (int)x_g8;
+    auto x_piece = [&](int it) -> uint2 {  // piece `it` of stage xl
+      const int h = x_single ? x_b3 : (it & 1);
+      const int mi = x_single ? 0 : (it >> 1) * 2 + x_b3;
+      const int kk = xl.sir * 1024 + x_koff + 4 * h;
+      if (xl.u < u_end && kk < p.k && mi < p.m) return *reinterpret_cast<const uint2*>(p.x + (int64_t)mi * p.k + kk);
+      return make_uint2(0u, 0u);
+    };
+    auto x_fill = [&](auto n_) {
+      constexpr int n = decltype(n_)::value;
+      if constexpr (!XRES) {
+#pragma unroll
+        for (int d = 0; d < C::XR / n; ++d) {
+#pragma unroll
+          for (int it = 0; it < n; ++it) xr[d * n + it] = x_piece(it);
+          xl.next(S);
+        }
+      }
+    };
+    // store the head stage's pieces into activation ring slot xs_seq % NX, shift, request the tail stage
+    auto x_step = [&](auto n_) {
+      constexpr int n = decltype(n_)::value;
+      if constexpr (!XRES) {
+        if (xs.u < u_end) {
+          const uint32_t xb = x0 + (xs_seq % C::NX) * C::kXStageBytes;
+#pragma unroll
+          for (int it = 0; it < n; ++it) {
+            uint32_t dst;
+            if (x_single) {
+              dst = xb + (uint32_t)x_s * 256u + (uint32_t)x_b3 * 64u + (uint32_t)x_j * 16u;
+            } else {
+              const uint32_t h = it & 1, grp = it >> 1;
+              dst = xb + ((uint32_t)(x_s * 2 + h) * x_g8 + grp) * x_pitch + (uint32_t)(x_b3 * 4 + x_j) * 16u;
+            }
+            x_put(dst, xr[it]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+          ++xs_seq;
+          xs.next(S);
+        }
+#pragma unroll
+        for (int i = 0; i + n < C::XR; ++i) xr[i] = xr[i + n];
+#pragma unroll
+        for (int it = 0; it < n; ++it) xr[C::XR - n + it] = x_piece(it);
+        xl.next(S);
+      }
+    };
     auto x_fill_any = [&]() {
       if constexpr (MB == 4) {
         if (x_nit == 1) x_fill(I1{});
@@ -507,14 +528,34 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
         x_step(IM{});
       }
     };
+    // resident activations (one row, all of k): stage t of the row -> half-lines [16t, 16t+16)
+    auto x_resident = [&]() {
+#pragma unroll 1
+      for (int t0 = 0; t0 < S; t0 += 4) {
+        uint2 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kk = (t0 + i) * 1024 + x_koff + 4 * x_b3;
+          v[i] = (t0 + i < S && kk < p.k) ? *reinterpret_cast<const uint2*>(p.x + kk) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (t0 + i < S) x_put(x0 + (uint32_t)((t0 + i) * 16 + x_s) * 256u + (uint32_t)x_b3 * 64u + (uint32_t)x_j * 16u, v[i]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+    };
+
     if (nsz == 1) sz_fill(I1{});
     else if (nsz == 2) sz_fill(I2{});
     else sz_fill(I4{});
 
-    int c = c_begin, rb = rb_first, cin = c_begin - rb_first * Cn;
-    while (c < c_end) {
-      const int len = min(Cn - cin, c_end - c);
-      const int nst = (len + 7) >> 3;
+    Cursor cur;
+    cur.init(u_begin, S);
+    const int rb_first = cur.rb;
+    while (cur.u < u_end) {
+      const int rb = cur.rb;
+      const int seg_first = cur.sir;
+      const int seg_n = min(S - cur.sir, u_end - cur.u);  // stages of this row block done by this CTA
       const int row0 = rb * 32;
 
       // ---- pair table of this row block ----
@@ -528,31 +569,33 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
             sts32(dst + (uint32_t)lo * 256u, prmt(tp_[lo >> 1], lut_hi[hh], (lo & 1) ? 0x5432u : 0x5410u));
         }
       }
-      if (c + len < c_end) load_lut(rb + 1);  // the next row block's LUT rows: a whole row block of time to arrive
+      if (cur.u + seg_n < u_end) load_lut(rb + 1);  // the next row block's LUT rows: a whole row block of time to arrive
       if (first_seg) {
         // the activations are the previous kernel's output: everything up to here overlapped its tail
         if (static_w) griddep_wait();
-        x_fill_any();
-        x_step_any();                  // stage 0's activations
+        if constexpr (XRES) {
+          x_resident();
+        } else {
+          x_fill_any();
+          x_step_any();  // stage 0's activations
+        }
         bar_sync(2, kDqThreads + 32);  // with the issuer warp: they are complete
       }
       bar_sync(1, kDqThreads);
       if (threadIdx.x == 0 && first_seg) TC_TRACE(2);
 
-      for (int st = 0; st < nst; ++st, ++gst) {
-        const int nvalid = min(8, len - st * 8);
-        const bool valid = warp < nvalid;
-        const int kt_valid = (p.k - (cin + st * 8 + warp) * 128) >> 4;  // k-tiles of this warp's chunk that exist (>= 8: all)
-        const int s = (int)(gst % kWStages);
+#pragma unroll 1
+      for (int i = 0; i < seg_n; ++i, ++gst) {
+        const int cc = (seg_first + i) * 8 + warp;  // this warp's chunk of the row
+        const int kt_valid = (p.k - cc * 128) >> 4;  // its k-tiles that exist (>= 8: all, <= 0: none)
         uint32_t s2[4], z2[4];
         if (nsz == 1) sz_step(I1{}, s2, z2);
         else if (nsz == 2) sz_step(I2{}, s2, z2);
         else sz_step(I4{}, s2, z2);
 
-        const uint32_t use = 2u * gst + (uint32_t)Q;  // A slot use (every stage serves both quads, see below)
-        const uint32_t acol = my_tmem + (uint32_t)(C::kABase + (int)(use % C::NS) * 64);
-        const uint32_t wb = sbase + wl_off + (uint32_t)s * kWStageStride;
-        wait_all(sbase + bar_off(B_WFULL + s), (gst / kWStages) & 1u);
+        const uint32_t acol = my_tmem + (uint32_t)C::kABase + as * 64u;
+        const uint32_t wb = sbase + wl_off + ws * kWStageStride;
+        if (!w_ready) mbar_wait(sbase + bar_off(B_WFULL) + ws * 8u, wpar);
         if (threadIdx.x == 0 && gst < 4) TC_TRACE(21 + gst * 4);
 
         // one k-tile (K step) of this lane's row: 8 byte lookups -> 8 TMEM columns
@@ -566,15 +609,20 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
             r[2 * q + 1] = lds_table(prmt(w, lane4, 0x7604u | (uint32_t)((b + 2) << 4)));
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) r[i] = fma2<DT>(r[i], s2[tp], z2[tp]);
+          for (int q = 0; q < 8; ++q) r[q] = fma2<DT>(r[q], s2[tp], z2[tp]);
         };
-        auto slot_wait = [&]() {  // the slot's previous use has been consumed (and with it all MMAs of stage gst - 2)
-          if (use >= (uint32_t)C::NS) {
-            wait_all(sbase + bar_off(B_AEMPTY + (int)(use % C::NS)), ((use / C::NS) - 1u) & 1u);
+        const bool no_wait = free_uses > 0;
+        auto slot_wait = [&]() {  // the slot's previous use has been consumed (and with it all MMAs of stage - 2)
+          if (!no_wait) {
+            if (!a_ready) mbar_wait(sbase + bar_off(B_AEMPTY) + as * 8u, apar ^ 1u);
             tc_fence_after();
           }
         };
-        if (valid && kt_valid >= 8) {
+        // next stage's ring slot; next use of this quad: slot (as + 2) % 3, phase of use + 2
+        const uint32_t ws_n = ws == 2u ? 0u : ws + 1u, wpar_n = ws == 2u ? wpar ^ 1u : wpar;
+        const uint32_t as_n = as == 0u ? 2u : as - 1u, apar_n = as == 0u ? apar : apar ^ 1u;
+        const bool more = cur.u + i + 1 < u_end;
+        if (kt_valid >= 8) {
           // the common case, straight-line: 4 x LDS.128, then per k-tile 8 x (PRMT, LDS.32, HFMA2) + one tcgen05.st
           uint32_t W[4][4];
           if constexpr (IK == 8) {
@@ -595,6 +643,8 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
               W[u][0] = v.x, W[u][1] = v.y, W[u][2] = v.z, W[u][3] = v.w;
             }
           }
+          // probe the next stage's weights now: the answer arrives while this stage's lookups issue
+          w_ready = more ? mbar_test(sbase + bar_off(B_WFULL) + ws_n * 8u, wpar_n) : 0u;
           uint32_t r0[8];
           k_step(W, 0, r0);  // overlaps the wait for the TMEM slot
           slot_wait();
@@ -606,13 +656,14 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
             tmem_st8(acol + (uint32_t)(T * 8), r);
           }
         } else {
-          // partial / missing chunk (segment tail, k tail): compact code, exact zeros where nothing exists.  A stage
-          // always serves both quads (uniform slot sequence), so a quad without chunks just writes zeros.
+          // partial / missing chunk (k tail): compact code, exact zeros where nothing exists.  A stage always serves
+          // both quads (uniform slot sequence), so a warp without a chunk just writes zeros.
+          w_ready = 0u;
           slot_wait();
 #pragma unroll 1
           for (int T = 0; T < 8; ++T) {
             uint32_t r[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            if (valid && T < kt_valid) {
+            if (T < kt_valid) {
               const int tp = T >> 1, b = T & 1;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -627,27 +678,33 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
               const uint32_t sv = tp == 0 ? s2[0] : tp == 1 ? s2[1] : tp == 2 ? s2[2] : s2[3];
               const uint32_t zv = tp == 0 ? z2[0] : tp == 1 ? z2[1] : tp == 2 ? z2[2] : z2[3];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) r[i] = fma2<DT>(r[i], sv, zv);
+              for (int q = 0; q < 8; ++q) r[q] = fma2<DT>(r[q], sv, zv);
             }
             tmem_st8(acol + (uint32_t)(T * 8), r);
           }
         }
-        x_step_any();  // stage gst+1's activations: their ring slot is free (see the kernel comment)
+        x_step_any();  // (streamed activations) stage + 1's pieces: their ring slot is free, see the kernel comment
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(sbase + bar_off(B_AFULL + (int)(use % C::NS)));
-          mbar_arrive(sbase + bar_off(B_WEMPTY + s));  // hand the weight stage back to the producer
+          mbar_arrive(sbase + bar_off(B_AFULL) + as * 8u);
+          mbar_arrive(sbase + bar_off(B_WEMPTY) + ws * 8u);  // hand the weight stage back to the producer
         }
+        if (free_uses > 0) --free_uses;
+        // probe this quad's next A slot (previous use: the OTHER quad's stage before ours); consumed one stage later
+        a_ready = (more && free_uses == 0) ? mbar_test(sbase + bar_off(B_AEMPTY) + as_n * 8u, apar_n ^ 1u) : 0u;
         if (threadIdx.x == 0 && gst < 4) TC_TRACE(22 + gst * 4);
+        ws = ws_n, wpar = wpar_n;
+        as = as_n, apar = apar_n;
       }
+      cur.skip(seg_n, S);
       if (threadIdx.x == 0 && first_seg) TC_TRACE(11);
 
       // ---- accumulators -> red[j][mi][lane] (quad 0's warps cover the four TMEM sub-partitions) ----
       if (Q == 0) {
         const int buf = (int)(dseq % C::NB);
-        wait_all(sbase + bar_off(B_DFULL + buf), (dseq / C::NB) & 1u);
+        mbar_wait(sbase + bar_off(B_DFULL + buf), (dseq / C::NB) & 1u);
         tc_fence_after();
         if (threadIdx.x == 0 && first_seg) TC_TRACE(12);
         const uint32_t dcol = my_tmem + (uint32_t)(buf * C::N + j);
@@ -667,7 +724,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       bar_sync(1, kDqThreads);
 
       // ---- row sums: thread idx -> (mi, row); the four quarters' partials added in order ----
-      const bool complete = (cin == 0 && len == Cn);
+      const bool complete = (seg_first == 0 && seg_n == S);
       const int rows_valid = min(32, p.w_rows - row0);
       auto emit = [&](int mi, int rr, float total) {
         if (p.flags & 16) {  // (gate, up) row pairs -> silu(gate) * up
@@ -697,8 +754,8 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
         float* mine = p.ws_partial + ((size_t)(me * 2 + slot) * 16) * 32;
         for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) __stcg(mine + idx, block_sum(idx >> 5, idx & 31));
         bar_sync(1, kDqThreads);
-        const int i_first = cta_of_chunk(p, rb * Cn);
-        const int i_last = cta_of_chunk(p, rb * Cn + Cn - 1);
+        const int i_first = cta_of_unit(p, rb * S);
+        const int i_last = cta_of_unit(p, rb * S + S - 1);
         volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(smem + kHolderOff + 4);
         if (threadIdx.x == 0) {
           unsigned old;
@@ -711,11 +768,11 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
         if (*flag) {
           for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) {
             float total = 0.f;
-            for (int i = i_first; i <= i_last; ++i) {
+            for (int ii = i_first; ii <= i_last; ++ii) {
               int b0, e0;
-              cta_range(p, i, b0, e0);
-              const int sl = (b0 / Cn == rb) ? 0 : 1;
-              total += __ldcg(p.ws_partial + ((size_t)(i * 2 + sl) * 16) * 32 + idx);
+              cta_range(p, ii, b0, e0);
+              const int sl = (b0 / S == rb) ? 0 : 1;
+              total += __ldcg(p.ws_partial + ((size_t)(ii * 2 + sl) * 16) * 32 + idx);
             }
             emit(idx >> 5, idx & 31, total);
           }
@@ -724,16 +781,13 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       }
       if (threadIdx.x == 0 && first_seg) TC_TRACE(13);
       first_seg = false;
-      c += len;
-      ++rb;
-      cin = 0;
     }
     if (threadIdx.x == 0) TC_TRACE(14);
   } else if (warp == kDqWarps) {
     // =============================================================== TMA producer: the rest of the stream
-    while (pit.valid(c_end)) {
+    while (pc.u < u_end) {
       const int s = (int)(pseq % kWStages);
-      wait_all(sbase + bar_off(B_WEMPTY + s), ((pseq / kWStages) - 1u) & 1u);
+      mbar_wait(sbase + bar_off(B_WEMPTY + s), ((pseq / kWStages) - 1u) & 1u);
       produce();
     }
   } else {
@@ -746,25 +800,25 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
     const uint32_t sbo = x_pitch;
     const uint32_t desc_hi = (sbo >> 4) | (1u << 14);  // descriptor version 1 (sm_100), no swizzle
     uint32_t gst = 0, dseq = 0;
-    bar_sync(2, kDqThreads + 32);  // stage 0's activations are staged
-    int c = c_begin, cin = c_begin - rb_first * Cn;
-    while (c < c_end) {
-      const int len = min(Cn - cin, c_end - c);
-      const int nst = (len + 7) >> 3;
+    bar_sync(2, kDqThreads + 32);  // the first activations are staged
+    Cursor cur;
+    cur.init(u_begin, S);
+    while (cur.u < u_end) {
+      const int seg_n = min(S - cur.sir, u_end - cur.u);
       const int buf = (int)(dseq % C::NB);
       if (dseq >= (uint32_t)C::NB) {
-        wait_all(sbase + bar_off(B_DEMPTY + buf), ((dseq / C::NB) - 1u) & 1u);
+        mbar_wait(sbase + bar_off(B_DEMPTY + buf), ((dseq / C::NB) - 1u) & 1u);
         tc_fence_after();
       }
       const uint32_t dcol = tmem + (uint32_t)(buf * C::N);
       uint32_t acc = 0;
-      for (int st = 0; st < nst; ++st, ++gst) {
-        const uint32_t xb = x0 + (gst % C::NX) * C::kXStageBytes;
+      for (int i = 0; i < seg_n; ++i, ++gst) {
+        const uint32_t xb = XRES ? x0 + (uint32_t)(cur.sir + i) * (16u * 256u) : x0 + (gst % C::NX) * C::kXStageBytes;
 #pragma unroll
         for (int Q = 0; Q < 2; ++Q) {
           const uint32_t use = 2u * gst + (uint32_t)Q;
           const int slot = (int)(use % C::NS);
-          wait_all(sbase + bar_off(B_AFULL + slot), (use / C::NS) & 1u);
+          mbar_wait(sbase + bar_off(B_AFULL + slot), (use / C::NS) & 1u);
           tc_fence_after();
           if (gst < 3 && Q == 0 && lane == 0) TC_TRACE(37 + gst * 3);
           __syncwarp();
@@ -781,7 +835,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
               acc = 1u;
             }
             tc_commit(sbase + bar_off(B_AEMPTY + slot));
-            if (Q == 1 && st == nst - 1) tc_commit(sbase + bar_off(B_DFULL + buf));  // the row block's sums are complete
+            if (Q == 1 && i == seg_n - 1) tc_commit(sbase + bar_off(B_DFULL + buf));  // the row block's sums are complete
           }
           acc = 1u;
           __syncwarp();
@@ -789,8 +843,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
         if (gst < 3 && lane == 0) TC_TRACE(38 + gst * 3);
       }
       ++dseq;
-      c += len;
-      cin = 0;
+      cur.skip(seg_n, S);
     }
   }
 
@@ -813,22 +866,22 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
   }
 }
 
-template <tg_dtype DT, int IK, int MB>
-__global__ void __launch_bounds__(Cfg<MB>::kThreads, Cfg<MB>::kMinBlocks) gemv_w4_tc_kernel(const ParamsTC p) {
-  gemv_w4_tc_body<DT, IK, MB, false>(p, Peers{});
+template <tg_dtype DT, int IK, int MB, bool XRES, bool MX4>
+__global__ void __launch_bounds__(Cfg<MB, XRES>::kThreads, Cfg<MB, XRES>::kMinBlocks) gemv_w4_tc_kernel(const ParamsTC p) {
+  gemv_w4_tc_body<DT, IK, MB, XRES, MX4, false>(p, Peers{});
 }
-// row-sharded variant: the epilogue stores into every rank's symmetric output buffer
-template <tg_dtype DT, int IK, int MB>
-__global__ void __launch_bounds__(Cfg<MB>::kThreads, Cfg<MB>::kMinBlocks) gemv_w4_tc_peer_kernel(const ParamsTC p,
-                                                                                               const __grid_constant__ Peers peers) {
-  gemv_w4_tc_body<DT, IK, MB, true>(p, peers);
+// row-sharded variant (decode kernels only): the epilogue stores into every rank's symmetric output buffer
+template <tg_dtype DT, int IK, int MB, bool XRES, bool MX4>
+__global__ void __launch_bounds__(Cfg<MB, XRES>::kThreads, Cfg<MB, XRES>::kMinBlocks)
+    gemv_w4_tc_peer_kernel(const ParamsTC p, const __grid_constant__ Peers peers) {
+  gemv_w4_tc_body<DT, IK, MB, XRES, MX4, true>(p, peers);
 }
 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 int g_ctas_per_sm = 0;  // 0 = heuristic (tuning: env TG_TC_CTAS)
-int g_split = -1;       // -1 = heuristic, 0 = whole row blocks per CTA, 1 = stream-K chunks (tuning: env TG_TC_SPLIT)
+int g_split = -1;       // -1 = heuristic, 0 = whole row blocks per CTA, 1 = stream-K over stages (tuning: env TG_TC_SPLIT)
 
 struct DeviceInfo {
   int n_sm = 0;
@@ -860,15 +913,17 @@ static int device_info(DeviceInfo** out) {
   return TG_OK;
 }
 
-template <tg_dtype DT, int IK, int MB>
+template <tg_dtype DT, int IK, int MB, bool XRES, bool MX4>
 int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) {
-  using C = Cfg<MB>;
-  auto kern = gemv_w4_tc_kernel<DT, IK, MB>;
-  auto kern_peer = gemv_w4_tc_peer_kernel<DT, IK, MB>;
+  using C = Cfg<MB, XRES>;
+  auto kern = gemv_w4_tc_kernel<DT, IK, MB, XRES, MX4>;
+  const void* kern_peer = nullptr;
+  if constexpr (MB == 4) kern_peer = (const void*)gemv_w4_tc_peer_kernel<DT, IK, MB, XRES, MX4>;
   static thread_local bool attr_set_dev[kMaxDevices] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
-    for (const void* f : {(const void*)kern, (const void*)kern_peer}) {
+    for (const void* f : {(const void*)kern, kern_peer}) {
+      if (f == nullptr) continue;
       if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem) != cudaSuccess ||
           cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) !=
               cudaSuccess) {
@@ -884,30 +939,30 @@ int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) 
 
   // Work split.  One CTA per SM while a CTA's share is small (the second slot of every SM is then free for the next
   // kernel of the stream, whose prologue overlaps our dequant), two per SM for the long ones (they hide each other's
-  // row-block boundaries).  Stream-K over 128-k chunks when that shortens the longest CTA by more than the fix-up
-  // of a shared row block costs (~kFixup chunks), else whole row blocks per CTA.
-  const int Cn = p.chunks_per_row;
-  const int64_t chunks = (int64_t)row_blocks * Cn;
+  // row-block boundaries).  Stream-K over ring stages when that shortens the longest CTA by more than the fix-up
+  // of a shared row block costs (~kFixup stages), else whole row blocks per CTA.
+  const int S = p.stages_per_row;
+  const int64_t stages = (int64_t)row_blocks * S;
   int per_sm = g_ctas_per_sm;
-  if (per_sm <= 0) per_sm = (chunks >= (int64_t)di->n_sm * 2 * 40) ? 2 : 1;
+  if (per_sm <= 0) per_sm = (stages >= (int64_t)di->n_sm * 2 * 5) ? 2 : 1;
   if (per_sm > C::kMinBlocks) per_sm = C::kMinBlocks;
   int64_t slots = (int64_t)di->n_sm * per_sm;
   if (slots > kMaxGrid) slots = kMaxGrid;
-  constexpr int64_t kFixup = 6;
-  const int64_t g_split_ctas = chunks < slots ? chunks : slots;
+  constexpr int64_t kFixup = 1;
+  const int64_t g_split_ctas = stages < slots ? stages : slots;
   const int64_t g_whole_ctas = row_blocks < slots ? row_blocks : slots;
-  const int64_t t_split = div_up(chunks, g_split_ctas) + kFixup;
-  const int64_t t_whole = div_up(row_blocks, g_whole_ctas) * Cn;
+  const int64_t t_split = div_up(stages, g_split_ctas) + kFixup;
+  const int64_t t_whole = div_up(row_blocks, g_whole_ctas) * S;
   const bool split = g_split >= 0 ? g_split != 0 : t_split < t_whole;
   int64_t G;
   if (split) {
     G = g_split_ctas;
     p.ug = 1;
-    p.cq = (int)(chunks / G);
-    p.cr = (int)(chunks % G);
+    p.cq = (int)(stages / G);
+    p.cr = (int)(stages % G);
   } else {
     G = g_whole_ctas;
-    p.ug = Cn;
+    p.ug = S;
     p.cq = (int)(row_blocks / G);
     p.cr = (int)(row_blocks % G);
   }
@@ -930,7 +985,17 @@ int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) 
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t e = peers.n > 0 ? cudaLaunchKernelEx(&cfg, kern_peer, p, peers) : cudaLaunchKernelEx(&cfg, kern, p);
+  cudaError_t e;
+  if (peers.n > 0) {
+    if constexpr (MB == 4) {
+      e = cudaLaunchKernelEx(&cfg, gemv_w4_tc_peer_kernel<DT, IK, MB, XRES, MX4>, p, peers);
+    } else {
+      set_error("row-sharded epilogue: at most 4 activation rows per pass");
+      return TG_ERR_UNSUPPORTED;
+    }
+  } else {
+    e = cudaLaunchKernelEx(&cfg, kern, p);
+  }
   if (e != cudaSuccess) {
     set_error("gemv_w4_tc launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -940,30 +1005,32 @@ int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) 
   return TG_OK;
 }
 
-template <tg_dtype DT, int IK>
+template <tg_dtype DT, int IK, bool MX4>
 int launch_m(ParamsTC p, const Peers& peers0, int row_blocks, int64_t rows_x, const uint16_t* x, uint16_t* y, cudaStream_t st) {
   Peers peers = peers0;
-  for (int64_t r0 = 0; r0 < rows_x; r0 += 16) {  // one pass carries up to 16 activation rows
-    p.m = (int)((rows_x - r0) < 16 ? (rows_x - r0) : 16);
+  const int per_pass = peers0.n > 0 ? 4 : 16;  // one pass carries up to 16 activation rows (4 with the peer-store epilogue)
+  for (int64_t r0 = 0; r0 < rows_x; r0 += per_pass) {
+    p.m = (int)((rows_x - r0) < per_pass ? (rows_x - r0) : per_pass);
     p.x = x + r0 * p.k;
     p.y = y + r0 * p.y_stride;
     for (int r = 0; r < peers0.n; ++r) peers.y[r] = peers0.y[r] + r0 * p.y_stride;
     int rc;
-    if (p.m <= 4) rc = launch_one<DT, IK, 4>(p, peers, row_blocks, st);
-    else if (p.m <= 8) rc = launch_one<DT, IK, 8>(p, peers, row_blocks, st);
-    else rc = launch_one<DT, IK, 16>(p, peers, row_blocks, st);
+    if (p.m == 1 && p.stages_per_row <= kXResMaxStages) rc = launch_one<DT, IK, 4, true, MX4>(p, peers, row_blocks, st);
+    else if (p.m <= 4) rc = launch_one<DT, IK, 4, false, MX4>(p, peers, row_blocks, st);
+    else if (p.m <= 8) rc = launch_one<DT, IK, 8, false, MX4>(p, peers, row_blocks, st);
+    else rc = launch_one<DT, IK, 16, false, MX4>(p, peers, row_blocks, st);
     if (rc != TG_OK) return rc;
   }
   return TG_OK;
 }
 
-template <tg_dtype DT>
+template <tg_dtype DT, bool MX4>
 int launch_ik(const ParamsTC& p, const Peers& peers, int ik, int row_blocks, int64_t rows_x, const uint16_t* x, uint16_t* y,
               cudaStream_t st) {
   switch (ik) {
-    case 2: return launch_m<DT, 2>(p, peers, row_blocks, rows_x, x, y, st);
-    case 4: return launch_m<DT, 4>(p, peers, row_blocks, rows_x, x, y, st);
-    case 8: return launch_m<DT, 8>(p, peers, row_blocks, rows_x, x, y, st);
+    case 2: return launch_m<DT, 2, MX4>(p, peers, row_blocks, rows_x, x, y, st);
+    case 4: return launch_m<DT, 4, MX4>(p, peers, row_blocks, rows_x, x, y, st);
+    case 8: return launch_m<DT, 8, MX4>(p, peers, row_blocks, rows_x, x, y, st);
   }
   set_error("B-layout int4 innerKTiles must be 2, 4 or 8 (got %d)", ik);
   return TG_ERR_INVALID_ARGUMENT;
@@ -995,18 +1062,21 @@ int launch_gemm_w4_tc_B(void* y, const void* x, const int32_t* w, const void* sz
     p.lut_stride = 0;
   }
   p.chunks_per_row = (int)div_up(k, 128);
+  p.stages_per_row = (int)div_up(k, 1024);
   const int64_t row_blocks = div_up(w_rows, 32);
-  if (row_blocks * p.chunks_per_row >= (1ll << 31)) {
-    set_error("w_rows * k = %lld * %lld exceeds the 2^43 elements one launch can index", (long long)w_rows, (long long)k);
+  if (row_blocks * p.stages_per_row >= (1ll << 31)) {
+    set_error("w_rows * k = %lld * %lld exceeds what one launch can index", (long long)w_rows, (long long)k);
     return TG_ERR_UNSUPPORTED;
   }
   p.flags = (w4::g_static_weights ? 8 : 0) | (silu_pairs ? 16 : 0);
 #ifdef TG_W4_TRACE
   p.trace = w4::g_trace_buf;
 #endif
-  if (dt == TG_BF16)
-    return tc::launch_ik<TG_BF16>(p, peers, ik, (int)row_blocks, rows_x, (const uint16_t*)x, (uint16_t*)y, st);
-  return tc::launch_ik<TG_FP16>(p, peers, ik, (int)row_blocks, rows_x, (const uint16_t*)x, (uint16_t*)y, st);
+  const uint16_t* xx = (const uint16_t*)x;
+  uint16_t* yy = (uint16_t*)y;
+  if (fmt == TG_W4_MX4) return tc::launch_ik<TG_BF16, true>(p, peers, ik, (int)row_blocks, rows_x, xx, yy, st);  // bf16 only
+  if (dt == TG_BF16) return tc::launch_ik<TG_BF16, false>(p, peers, ik, (int)row_blocks, rows_x, xx, yy, st);
+  return tc::launch_ik<TG_FP16, false>(p, peers, ik, (int)row_blocks, rows_x, xx, yy, st);
 }
 
 void set_tc_ctas_per_sm(int v) { tc::g_ctas_per_sm = v; }

@@ -70,6 +70,38 @@ __device__ __forceinline__ unsigned long long run_slots(uint32_t tmem_lane, uint
   return clock64() - t0;
 }
 
+__global__ void __launch_bounds__(576, 1) probe3(uint32_t nwarps, unsigned long long* __restrict__ out, uint32_t* __restrict__ sink_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t holder = sbase + 65536 + 49536;
+  const uint32_t bar = holder + 16;
+  for (int i = threadIdx.x; i < (65536 + 49536) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = i * 2654435761u;
+  if (warp == 16) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 100000;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + 65536 + 49536);
+  uint32_t sink = 0;
+  if (warp < (int)nwarps) {
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 32;
+    const uint32_t wbase = sbase + 65536 + (warp & 7) * 512 + lane * 32;
+    unsigned long long c3 = run_slots<3>(tl, wbase, lane * 4, bar, sink);
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = c3 / kIters;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  if (sink == 0x12345u) sink_out[threadIdx.x] = sink;
+}
+
 __global__ void __launch_bounds__(352, 2) probe2(const uint8_t* __restrict__ gsrc, unsigned long long* __restrict__ out,
                                                  uint32_t* __restrict__ sink_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -178,6 +210,17 @@ int main() {
     printf("grid %3d: cycles per slot (8 warps): lookups+fma %llu | +STTM %llu | +wait::st %llu | +fence+arrive %llu || fence.proxy.async %llu | "
            "try_wait(done) %llu | bulk 4K issue %llu (8 copies landed after %llu)\n",
            grid, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[8]);
+  }
+  cudaFuncSetAttribute(probe3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int nw : {1, 2, 4, 6, 8, 12, 16}) {
+    probe3<<<148, 576, smem>>>(nw, d_out, d_sink);
+    cudaDeviceSynchronize();
+    probe3<<<148, 576, smem>>>(nw, d_out, d_sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+    unsigned long long h[1];
+    cudaMemcpy(h, d_out, 8, cudaMemcpyDeviceToHost);
+    printf("one CTA/SM, %2d dequant warps: %llu cycles per 32-lookup slot per warp -> %.1f nibbles/clk/SM\n", nw, h[0], nw * 2048.0 / h[0]);
   }
   return 0;
 }

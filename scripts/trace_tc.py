@@ -48,18 +48,42 @@ def main():
         w, lut, sz = layers[0]
         w1, lut1, sz1 = layers[1]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if os.environ.get("TR_PREV", "0") == "1":
-            op(x, w1, G, sz1, lut1, True)
-        lib.tg_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
-        e0.record()
-        op(x, w, G, sz, lut, True)
-        e1.record()
-        lib.tg_debug_set_trace(None)
-        torch.cuda.synchronize()
+        buf0 = torch.zeros(ctas * 64, dtype=torch.int64, device=dev)
+        if os.environ.get("TR_GRAPH", "0") == "1":
+            # three GEMVs in one CUDA graph (programmatic edges): trace the 2nd and the 3rd
+            w2, lut2, sz2 = layers[2]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                lib.tg_debug_set_trace(None)
+                op(x, w2, G, sz2, lut2, True)
+                lib.tg_debug_set_trace(ctypes.c_void_p(buf0.data_ptr()))
+                op(x, w1, G, sz1, lut1, True)
+                lib.tg_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
+                op(x, w, G, sz, lut, True)
+                lib.tg_debug_set_trace(None)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+        else:
+            if os.environ.get("TR_PREV", "0") == "1":
+                lib.tg_debug_set_trace(ctypes.c_void_p(buf0.data_ptr()))
+                op(x, w1, G, sz1, lut1, True)
+            lib.tg_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
+            e0.record()
+            op(x, w, G, sz, lut, True)
+            e1.record()
+            lib.tg_debug_set_trace(None)
+            torch.cuda.synchronize()
         t = buf.cpu().numpy().reshape(ctas, 64).astype(np.int64)
         t = t[t[:, 0] > 0]
         ctas = len(t)
         t0 = t[:, 0].min()
+        if os.environ.get("TR_PREV", "0") == "1" or os.environ.get("TR_GRAPH", "0") == "1":
+            tp = buf0.cpu().numpy().reshape(-1, 64).astype(np.int64)
+            tp = tp[tp[:, 0] > 0]
+            print(f"previous kernel: entry {np.median(tp[:, 0] - t0) / 1e3:.2f} us, x staged {np.median(tp[:, 2] - t0) / 1e3:.2f}, "
+                  f"exit median {np.median(tp[:, 48] - t0) / 1e3:.2f} max {(tp[:, 48].max() - t0) / 1e3:.2f} (relative to this kernel's first entry)")
         rel = (t - t0) / 1e3
         rel[t == 0] = np.nan
         print(f"== n=k={n} m={m}: {ctas} CTAs, event time {e0.elapsed_time(e1) * 1e3:.1f} us, SMs used {len(set(t[:, 63]))}")
