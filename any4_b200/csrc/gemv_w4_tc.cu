@@ -165,6 +165,7 @@ struct Cfg {
   static constexpr int kThreads = kWarps * 32;
   static constexpr int kABase = NB * N;            // TMEM: accumulators first, then the A slots
   static constexpr int kRedHl0 = XRES ? 224 : (MB == 4 ? 192 : 0);  // reduction scratch [4][MB] half-lines
+  static constexpr int kLutHl0 = XRES ? 243 : (MB == 4 ? 208 : 64);  // next row block's LUT rows (8 half-lines)
   static constexpr uint32_t kXStageBytes = MB == 4 ? 64u * 256u : 32u * (MB / 2) * 128u;
   static constexpr uint32_t kSmem = MB == 4 ? kXDenseOff : kXDenseOff + NX * kXStageBytes;
   static constexpr int kMinBlocks = MB == 4 ? 2 : 1;
@@ -280,11 +281,13 @@ struct Cursor {
 // of stage i; an A slot is refilled only after the commit of its previous use, which (one issuer: commits are
 // cumulative) also proves that the MMAs of stage i-2 are done, i.e. that activation ring slot (i+1) % 3 is free.
 // ---------------------------------------------------------------------------------------
-template <tg_dtype DT, int IK, int MB, bool XRES, bool MX4, bool PEERS>
+template <tg_dtype DT, int IK, int MB, bool XRES, bool MX4, bool G128, bool PEERS>
 __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& peers) {
   using C = Cfg<MB, XRES>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t sbase = smem_u32(smem);
+  // the dynamic shared window of a kernel without static shared memory starts at kSmemBase (checked right below):
+  // every shared address in this kernel is that constant plus an offset, so most of them fold into immediates
+  constexpr uint32_t sbase = kSmemBase;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
 
@@ -295,7 +298,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const bool static_w = (p.flags & 8) != 0;
   if (threadIdx.x == 0) TC_TRACE(0);
-  if (sbase != kSmemBase) __trap();  // lds_table() relies on it
+  if (smem_u32(smem) != kSmemBase) __trap();
   if (!static_w) griddep_wait();
 
   int u_begin, u_end;
@@ -316,6 +319,15 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
   const uint32_t x_g8 = MB == 4 ? (p.m > 2 ? 2u : 1u) : (uint32_t)(MB / 2);
   const uint32_t x_pitch = MB == 4 ? 256u : 128u;
   const uint32_t x0 = sbase + (MB == 4 ? 128u : kXDenseOff);
+  // staging: a lane pair (f = lane & 1) holds x[k0 + 4h ..+3] (f = 0) and x[k0 + 8 + 4h ..+3] (f = 1) and turns them
+  // into the 16-byte unit (lo0,hi0,lo1,hi1,lo2,hi2,lo3,hi3): lane 0 writes the first 8 bytes (needs the partner's .x),
+  // lane 1 the rest
+  const int x_f = lane & 1;
+  auto x_put = [&](uint32_t dst, uint2 v) {
+    const uint32_t got = __shfl_xor_sync(0xffffffffu, x_f ? v.x : v.y, 1);
+    const uint32_t a = x_f ? got : v.x, b = x_f ? v.y : got;
+    sts64(dst + (uint32_t)x_f * 8u, prmt(a, b, 0x5410u), prmt(a, b, 0x7632u));
+  };
 
   // ------------------------------------------------------------------ setup
   Cursor pc;  // producer cursor (warp 8)
@@ -338,16 +350,18 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
     ++pseq;
     pc.next(S);
   };
-  uint4 lut0 = make_uint4(0, 0, 0, 0), lut1 = lut0;
-  uint32_t lut_hi[2] = {0u, 0u};
   const int rl = row_of_lane(lane);  // the weight row (within the block) this lane owns
-  auto load_lut = [&](int rb) {
-    const int row = min(rb * 32 + rl, p.w_rows - 1);
-    const uint16_t* lrow = p.lut + (int64_t)row * p.lut_stride;
-    lut0 = *reinterpret_cast<const uint4*>(lrow);
-    lut1 = *reinterpret_cast<const uint4*>(lrow + 8);
-    lut_hi[0] = (uint32_t)lrow[2 * warp];  // this warp builds the 32 table entries whose high nibble is 2w, 2w+1
-    lut_hi[1] = (uint32_t)lrow[2 * warp + 1];
+  // The LUT rows of a row block (32 x 32 B) travel global -> shared memory with cp.async (no registers, no stall):
+  // requested one row block ahead, read back when the pair table is built.  Threads 0..63 copy 16 bytes each.
+  auto request_lut = [&](int rb) {
+    if (threadIdx.x < 64) {
+      const int r = (int)threadIdx.x >> 1;
+      const int row = min(rb * 32 + r, p.w_rows - 1);
+      const uint16_t* src = p.lut + (int64_t)row * p.lut_stride + (threadIdx.x & 1) * 8;
+      const uint32_t dst = sbase + odd_hl(C::kLutHl0 + (r >> 2)) + (uint32_t)(r & 3) * 32u + (threadIdx.x & 1) * 16u;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   if (warp == kDqWarps) {
@@ -375,7 +389,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else {
-    load_lut(u_begin / S);  // in flight across the setup barrier
+    request_lut(u_begin / S);  // in flight across the setup barrier
   }
   tc_fence_before();
   __syncthreads();
@@ -402,9 +416,11 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
     // pieces - travel through REGISTER RINGS filled several stages ahead: a stage consumes the head, shifts, and
     // requests the stage `depth` ahead at the tail.  Depth = ring size / values per stage.
 
-    // ---- group words: nsz per stage (1: group >= 128, 2: group 64, 4: group 32), ring of 8 -> 8 / 4 / 2 stages ----
-    const int nsz = p.glog2 >= 7 ? 1 : (p.glog2 == 6 ? 2 : 4);
-    uint32_t szr[8];
+    // ---- group words ----
+    // G128 (group >= 128: one word per stage): ring of 4, one load per stage; else nsz = 2 (group 64) or 4 (group 32)
+    // words per stage in a ring of 8 (4 / 2 stages ahead).
+    const int nsz = (G128 || p.glog2 >= 7) ? 1 : (p.glog2 == 6 ? 2 : 4);
+    uint32_t szr[G128 ? 4 : 8];
     Cursor zc;
     zc.init(u_begin, S);
     auto sz_word = [&](int t, int n) -> uint32_t {  // word t of n for this warp's chunk of stage zc
@@ -415,10 +431,11 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       if constexpr (MX4) return e8m0_to_dt<DT>((uint32_t)p.exps[(int64_t)row * n_groups + gi]) | 0x80000000u;  // zero = -0
       else return p.sz[(int64_t)gi * p.w_rows + row];
     };
-    auto sz_fill = [&](auto n_) {  // prologue: the first 8 / n stages
+    auto sz_fill = [&](auto n_) {  // prologue: the first stages
       constexpr int n = decltype(n_)::value;
+      constexpr int R = G128 ? 4 : 8;
 #pragma unroll
-      for (int d = 0; d < 8 / n; ++d) {
+      for (int d = 0; d < R / n; ++d) {
 #pragma unroll
         for (int t = 0; t < n; ++t) szr[d * n + t] = sz_word(t, n);
         zc.next(S);
@@ -427,6 +444,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
     // consume this stage's words into (s, s) / (z, z) pairs for the four 32-k quarters, shift, request the tail stage
     auto sz_step = [&](auto n_, uint32_t (&s2)[4], uint32_t (&z2)[4]) {
       constexpr int n = decltype(n_)::value;
+      constexpr int R = G128 ? 4 : 8;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const uint32_t v = szr[t * n / 4];
@@ -434,9 +452,9 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
         z2[t] = prmt(v, v, 0x3232u);
       }
 #pragma unroll
-      for (int i = 0; i + n < 8; ++i) szr[i] = szr[i + n];
+      for (int i = 0; i + n < R; ++i) szr[i] = szr[i + n];
 #pragma unroll
-      for (int t = 0; t < n; ++t) szr[8 - n + t] = sz_word(t, n);
+      for (int t = 0; t < n; ++t) szr[R - n + t] = sz_word(t, n);
       zc.next(S);
     };
     using I1 = std::integral_constant<int, 1>;
@@ -447,16 +465,9 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
     // ---- activation staging: thread (warp w, lane) owns the 8-byte pieces f of the units (s = 2w + slo, h, n) ----
     // lane = f | j<<1 | (h or mi&1)<<3 | slo<<4: a half-warp writes one contiguous 128-byte half-line (conflict free)
     // and reads whole 32-byte sectors of x.  Pieces per stage: 1 (m = 1), 2 (m = 2), 4 (m = 3, 4), MB (MB >= 8).
-    const int x_f = lane & 1, x_j = (lane >> 1) & 3, x_b3 = (lane >> 3) & 1, x_s = 2 * warp + (lane >> 4);
+    const int x_j = (lane >> 1) & 3, x_b3 = (lane >> 3) & 1, x_s = 2 * warp + (lane >> 4);
     const int x_ch = (x_s >> 3) * 4 + x_j;                     // chunk of the stage
     const int x_koff = x_ch * 128 + (x_s & 7) * 16 + 8 * x_f;  // + 4h
-    // the pair (lane f = 0: x[k0 + 4h ..+3], lane f = 1: x[k0 + 8 + 4h ..+3]) becomes the 16-byte unit
-    // (lo0,hi0,lo1,hi1,lo2,hi2,lo3,hi3): lane 0 writes its first 8 bytes (needs the partner's .x), lane 1 the rest
-    auto x_put = [&](uint32_t dst, uint2 v) {
-      const uint32_t got = __shfl_xor_sync(0xffffffffu, x_f ? v.x : v.y, 1);
-      const uint32_t a = x_f ? got : v.x, b = x_f ? v.y : got;
-      sts64(dst + (uint32_t)x_f * 8u, prmt(a, b, 0x5410u), prmt(a, b, 0x7632u));
-    };
     // streamed activations
     Cursor xl, xs;
     xl.init(u_begin, S);
@@ -528,24 +539,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
         x_step(IM{});
       }
     };
-    // resident activations (one row, all of k): stage t of the row -> half-lines [16t, 16t+16)
-    auto x_resident = [&]() {
-#pragma unroll 1
-      for (int t0 = 0; t0 < S; t0 += 4) {
-        uint2 v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int kk = (t0 + i) * 1024 + x_koff + 4 * x_b3;
-          v[i] = (t0 + i < S && kk < p.k) ? *reinterpret_cast<const uint2*>(p.x + kk) : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (t0 + i < S) x_put(x0 + (uint32_t)((t0 + i) * 16 + x_s) * 256u + (uint32_t)x_b3 * 64u + (uint32_t)x_j * 16u, v[i]);
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
-    };
-
-    if (nsz == 1) sz_fill(I1{});
+    if (G128 || nsz == 1) sz_fill(I1{});
     else if (nsz == 2) sz_fill(I2{});
     else sz_fill(I4{});
 
@@ -558,30 +552,35 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       const int seg_n = min(S - cur.sir, u_end - cur.u);  // stages of this row block done by this CTA
       const int row0 = rb * 32;
 
-      // ---- pair table of this row block ----
+      // ---- pair table of this row block (its LUT rows were requested one row block ago) ----
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      bar_sync(1, kDqThreads);  // LUT rows landed; everybody is done with the previous table
       {
-        const uint32_t tp_[8] = {lut0.x, lut0.y, lut0.z, lut0.w, lut1.x, lut1.y, lut1.z, lut1.w};
+        const uint32_t lrow = sbase + odd_hl(C::kLutHl0 + (rl >> 2)) + (uint32_t)(rl & 3) * 32u;
+        const uint4 l0 = lds128(lrow), l1 = lds128(lrow + 16u);
+        const uint32_t tp_[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const uint32_t hw = lds32(lrow + (uint32_t)warp * 4u);  // entries 2w, 2w+1: this warp builds the table
+                                                                // entries whose high nibble is 2w / 2w+1
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t hi = hh ? hw >> 16 : hw;
           const uint32_t dst = sbase + (uint32_t)((2 * warp + hh) * 16) * 256u + lane4;
 #pragma unroll
           for (int lo = 0; lo < 16; ++lo)
-            sts32(dst + (uint32_t)lo * 256u, prmt(tp_[lo >> 1], lut_hi[hh], (lo & 1) ? 0x5432u : 0x5410u));
+            sts32(dst + (uint32_t)lo * 256u, prmt(tp_[lo >> 1], hi, (lo & 1) ? 0x5432u : 0x5410u));
         }
       }
-      if (cur.u + seg_n < u_end) load_lut(rb + 1);  // the next row block's LUT rows: a whole row block of time to arrive
-      if (first_seg) {
-        // the activations are the previous kernel's output: everything up to here overlapped its tail
-        if (static_w) griddep_wait();
-        if constexpr (XRES) {
-          x_resident();
-        } else {
+      bar_sync(1, kDqThreads);  // table complete, LUT staging area free again
+      if (cur.u + seg_n < u_end) request_lut(rb + 1);
+      if constexpr (!XRES) {
+        if (first_seg) {
+          // the activations are the previous kernel's output: everything up to here overlapped its tail
+          if (static_w) griddep_wait();
           x_fill_any();
-          x_step_any();  // stage 0's activations
+          x_step_any();                  // stage 0's activations
+          bar_sync(2, kDqThreads + 32);  // with the issuer warp: they are complete
         }
-        bar_sync(2, kDqThreads + 32);  // with the issuer warp: they are complete
       }
-      bar_sync(1, kDqThreads);
       if (threadIdx.x == 0 && first_seg) TC_TRACE(2);
 
 #pragma unroll 1
@@ -589,7 +588,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
         const int cc = (seg_first + i) * 8 + warp;  // this warp's chunk of the row
         const int kt_valid = (p.k - cc * 128) >> 4;  // its k-tiles that exist (>= 8: all, <= 0: none)
         uint32_t s2[4], z2[4];
-        if (nsz == 1) sz_step(I1{}, s2, z2);
+        if (G128 || nsz == 1) sz_step(I1{}, s2, z2);
         else if (nsz == 2) sz_step(I2{}, s2, z2);
         else sz_step(I4{}, s2, z2);
 
@@ -800,7 +799,39 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
     const uint32_t sbo = x_pitch;
     const uint32_t desc_hi = (sbo >> 4) | (1u << 14);  // descriptor version 1 (sm_100), no swizzle
     uint32_t gst = 0, dseq = 0;
-    bar_sync(2, kDqThreads + 32);  // the first activations are staged
+    uint32_t x_staged = 0;  // resident activations: bit t = stage t of the row is in shared memory
+    // Resident activations (one row, all of k; stage t of the row -> half-lines [16t, 16t+16)) are staged by THIS warp,
+    // so the dequant warps never wait for the previous kernel: they fill the TMEM slots while it is still running.
+    // Up to 4 stages (32 eight-byte pieces per lane) are requested together; each is stored right before its first
+    // MMA, so the first MMA waits for one load latency only.
+    uint2 xv[4][8];      // pieces of up to four row stages [xv_t0, xv_t0 + xv_n), requested together
+    int xv_t0 = 0, xv_n = 0;
+    const int xl_j = (lane >> 1) & 3, xl_b3 = (lane >> 3) & 1, xl_hi = lane >> 4;
+    auto x_request = [&](int t0, int n) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int xs_ = 2 * q + xl_hi;
+          const int kk = (t0 + i) * 1024 + ((xs_ >> 3) * 4 + xl_j) * 128 + (xs_ & 7) * 16 + 8 * x_f + 4 * xl_b3;
+          xv[i][q] = (i < n && kk < p.k) ? *reinterpret_cast<const uint2*>(p.x + kk) : make_uint2(0u, 0u);
+        }
+      xv_t0 = t0, xv_n = n;
+    };
+    auto x_store_stage = [&](int t, const uint2 (&v)[8]) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        x_put(x0 + (uint32_t)(t * 16 + 2 * q + xl_hi) * 256u + (uint32_t)xl_b3 * 64u + (uint32_t)xl_j * 16u, v[q]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+      __syncwarp();
+    };
+    if constexpr (XRES) {
+      if (lane == 0) TC_TRACE(50);
+      if (static_w) griddep_wait();  // the activations are the previous kernel's output
+      if (lane == 0) TC_TRACE(51);
+    } else {
+      bar_sync(2, kDqThreads + 32);  // the first activations are staged (by the dequant warps)
+    }
     Cursor cur;
     cur.init(u_begin, S);
     while (cur.u < u_end) {
@@ -814,6 +845,24 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       uint32_t acc = 0;
       for (int i = 0; i < seg_n; ++i, ++gst) {
         const uint32_t xb = XRES ? x0 + (uint32_t)(cur.sir + i) * (16u * 256u) : x0 + (gst % C::NX) * C::kXStageBytes;
+        if constexpr (XRES) {
+          const int t = cur.sir + i;
+          if (!((x_staged >> t) & 1u)) {
+            if (t < xv_t0 || t >= xv_t0 + xv_n) {  // not requested yet: this and the next unstaged stages of the row
+              int n = 1;
+              while (n < 4 && t + n < S && !((x_staged >> (t + n)) & 1u)) ++n;
+              x_request(t, n);
+            }
+            switch (t - xv_t0) {  // store only the stage needed now; the others' loads keep flying
+              case 0: x_store_stage(t, xv[0]); break;
+              case 1: x_store_stage(t, xv[1]); break;
+              case 2: x_store_stage(t, xv[2]); break;
+              default: x_store_stage(t, xv[3]); break;
+            }
+            if (lane == 0 && x_staged == 0) TC_TRACE(52);
+            x_staged |= 1u << t;
+          }
+        }
 #pragma unroll
         for (int Q = 0; Q < 2; ++Q) {
           const uint32_t use = 2u * gst + (uint32_t)Q;
@@ -866,15 +915,15 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
   }
 }
 
-template <tg_dtype DT, int IK, int MB, bool XRES, bool MX4>
+template <tg_dtype DT, int IK, int MB, bool XRES, bool MX4, bool G128>
 __global__ void __launch_bounds__(Cfg<MB, XRES>::kThreads, Cfg<MB, XRES>::kMinBlocks) gemv_w4_tc_kernel(const ParamsTC p) {
-  gemv_w4_tc_body<DT, IK, MB, XRES, MX4, false>(p, Peers{});
+  gemv_w4_tc_body<DT, IK, MB, XRES, MX4, G128, false>(p, Peers{});
 }
 // row-sharded variant (decode kernels only): the epilogue stores into every rank's symmetric output buffer
-template <tg_dtype DT, int IK, int MB, bool XRES, bool MX4>
+template <tg_dtype DT, int IK, int MB, bool XRES, bool MX4, bool G128>
 __global__ void __launch_bounds__(Cfg<MB, XRES>::kThreads, Cfg<MB, XRES>::kMinBlocks)
     gemv_w4_tc_peer_kernel(const ParamsTC p, const __grid_constant__ Peers peers) {
-  gemv_w4_tc_body<DT, IK, MB, XRES, MX4, true>(p, peers);
+  gemv_w4_tc_body<DT, IK, MB, XRES, MX4, G128, true>(p, peers);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -913,12 +962,12 @@ static int device_info(DeviceInfo** out) {
   return TG_OK;
 }
 
-template <tg_dtype DT, int IK, int MB, bool XRES, bool MX4>
+template <tg_dtype DT, int IK, int MB, bool XRES, bool MX4, bool G128>
 int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) {
   using C = Cfg<MB, XRES>;
-  auto kern = gemv_w4_tc_kernel<DT, IK, MB, XRES, MX4>;
+  auto kern = gemv_w4_tc_kernel<DT, IK, MB, XRES, MX4, G128>;
   const void* kern_peer = nullptr;
-  if constexpr (MB == 4) kern_peer = (const void*)gemv_w4_tc_peer_kernel<DT, IK, MB, XRES, MX4>;
+  if constexpr (MB == 4) kern_peer = (const void*)gemv_w4_tc_peer_kernel<DT, IK, MB, XRES, MX4, G128>;
   static thread_local bool attr_set_dev[kMaxDevices] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
@@ -988,7 +1037,7 @@ int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) 
   cudaError_t e;
   if (peers.n > 0) {
     if constexpr (MB == 4) {
-      e = cudaLaunchKernelEx(&cfg, gemv_w4_tc_peer_kernel<DT, IK, MB, XRES, MX4>, p, peers);
+      e = cudaLaunchKernelEx(&cfg, gemv_w4_tc_peer_kernel<DT, IK, MB, XRES, MX4, G128>, p, peers);
     } else {
       set_error("row-sharded epilogue: at most 4 activation rows per pass");
       return TG_ERR_UNSUPPORTED;
@@ -1015,10 +1064,13 @@ int launch_m(ParamsTC p, const Peers& peers0, int row_blocks, int64_t rows_x, co
     p.y = y + r0 * p.y_stride;
     for (int r = 0; r < peers0.n; ++r) peers.y[r] = peers0.y[r] + r0 * p.y_stride;
     int rc;
-    if (p.m == 1 && p.stages_per_row <= kXResMaxStages) rc = launch_one<DT, IK, 4, true, MX4>(p, peers, row_blocks, st);
-    else if (p.m <= 4) rc = launch_one<DT, IK, 4, false, MX4>(p, peers, row_blocks, st);
-    else if (p.m <= 8) rc = launch_one<DT, IK, 8, false, MX4>(p, peers, row_blocks, st);
-    else rc = launch_one<DT, IK, 16, false, MX4>(p, peers, row_blocks, st);
+    const bool res = p.m == 1 && p.stages_per_row <= kXResMaxStages;
+    // the decode kernel (one activation row) is specialised for groups >= 128 (one group word per stage)
+    if (res && p.glog2 >= 7) rc = launch_one<DT, IK, 4, true, MX4, true>(p, peers, row_blocks, st);
+    else if (res) rc = launch_one<DT, IK, 4, true, MX4, false>(p, peers, row_blocks, st);
+    else if (p.m <= 4) rc = launch_one<DT, IK, 4, false, MX4, false>(p, peers, row_blocks, st);
+    else if (p.m <= 8) rc = launch_one<DT, IK, 8, false, MX4, false>(p, peers, row_blocks, st);
+    else rc = launch_one<DT, IK, 16, false, MX4, false>(p, peers, row_blocks, st);
     if (rc != TG_OK) return rc;
   }
   return TG_OK;

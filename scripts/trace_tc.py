@@ -23,6 +23,9 @@ for _i in range(4):
     NAMES[21 + 4 * _i] = f"st{_i}_wfull"
     NAMES[22 + 4 * _i] = f"st{_i}_slot0"
     NAMES[23 + 4 * _i] = f"st{_i}_slot1"
+NAMES[50] = "iss_before_dep"
+NAMES[51] = "iss_dep_ok"
+NAMES[52] = "iss_x_staged"
 for _i in range(3):
     NAMES[36 + 3 * _i] = f"iss{_i}_xfull"
     NAMES[37 + 3 * _i] = f"iss{_i}_afull"
