@@ -64,9 +64,8 @@ constexpr int kXResMaxStages = 14;          // resident activations: 16 half-lin
 constexpr int kMaxGrid = 512;
 constexpr int kWsPools = 4;
 
-// split fix-up workspace: fp32 partial sums [pool][CTA][slot 0/1][mi][row] and arrival counters
-__device__ float g_ws_partial[kWsPools][kMaxGrid * 2 * 16 * 32];
-__device__ unsigned g_ws_counter[kWsPools][kMaxGrid];
+// split fix-up workspace: tagged fp32 partial sums [pool][CTA][slot 0/1][mi][row], one 8-byte word (value, launch tag) each
+__device__ unsigned long long g_ws_partial[kWsPools][kMaxGrid * 2 * 16 * 32];
 
 struct ParamsTC {
   const uint8_t* w;      // packed weight
@@ -75,8 +74,8 @@ struct ParamsTC {
   const uint32_t* sz;    // [k/g][w_rows] (scale, zero) pairs (unused for mx4)
   const uint8_t* exps;   // [w_rows][k/g] e8m0, mx4 only
   const uint16_t* lut;   // [16] or [w_rows][16]
-  float* ws_partial;     // this launch's workspace pool
-  unsigned* ws_counter;
+  unsigned long long* ws_partial;  // this launch's workspace pool
+  uint32_t ws_tag;                  // launch tag carried by every partial of this launch
   int64_t tile_stride;   // bytes between consecutive n-tiles of the packed weight = 4 * k
   int64_t y_stride;
   int lut_stride;        // 0 or 16
@@ -745,38 +744,37 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       if (complete) {
         for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) emit(idx >> 5, idx & 31, block_sum(idx >> 5, idx & 31));
       } else {
-        // Row block shared with other CTAs: publish the fp32 partials, count arrivals; the last CTA to arrive adds
-        // the partials of all the block's CTAs in CTA order (deterministic) and stores the result.  Release /
-        // acquire at GPU scope on the counter (cumulative over the CTA barriers) orders the partials.
+        // Row block shared with other CTAs.  The CTA that holds the block's FIRST stages owns the result: that segment
+        // is the last thing the CTA does, while the other CTAs meet the block at the very beginning of their ranges,
+        // so their partials are long there.  A partial travels as ONE 8-byte word (value, launch tag): whoever sees
+        // the tag sees the value, so no fence, no atomic and no counter is needed (a fence would wait ~2 us for this
+        // thread's prefetched group words to come back behind the weight stream).  The owner adds the partials in CTA
+        // order: deterministic.
         const int me = (int)blockIdx.x;
-        const int slot = rb == rb_first ? 0 : 1;
-        float* mine = p.ws_partial + ((size_t)(me * 2 + slot) * 16) * 32;
-        for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) __stcg(mine + idx, block_sum(idx >> 5, idx & 31));
-        bar_sync(1, kDqThreads);
         const int i_first = cta_of_unit(p, rb * S);
         const int i_last = cta_of_unit(p, rb * S + S - 1);
-        volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(smem + kHolderOff + 4);
-        if (threadIdx.x == 0) {
-          unsigned old;
-          asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.ws_counter + i_first) : "memory");
-          const bool last = old == (unsigned)(i_last - i_first);
-          if (last) p.ws_counter[i_first] = 0u;  // self-resetting: ready for the next launch that uses this pool
-          *flag = last ? 1u : 0u;
-        }
-        bar_sync(1, kDqThreads);
-        if (*flag) {
-          for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) {
-            float total = 0.f;
-            for (int ii = i_first; ii <= i_last; ++ii) {
+        for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) {
+          float total = block_sum(idx >> 5, idx & 31);
+          if (me != i_first) {
+            const int slot = rb == rb_first ? 0 : 1;
+            const unsigned long long word = ((unsigned long long)p.ws_tag << 32) | (unsigned long long)__float_as_uint(total);
+            asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p.ws_partial + ((size_t)(me * 2 + slot) * 16) * 32 + idx), "l"(word)
+                         : "memory");
+          } else {
+            for (int ii = i_first + 1; ii <= i_last; ++ii) {
               int b0, e0;
               cta_range(p, ii, b0, e0);
               const int sl = (b0 / S == rb) ? 0 : 1;
-              total += __ldcg(p.ws_partial + ((size_t)(ii * 2 + sl) * 16) * 32 + idx);
+              const unsigned long long* src = p.ws_partial + ((size_t)(ii * 2 + sl) * 16) * 32 + idx;
+              unsigned long long word;
+              do {
+                asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(word) : "l"(src) : "memory");
+              } while ((uint32_t)(word >> 32) != p.ws_tag);
+              total += __uint_as_float((uint32_t)word);
             }
             emit(idx >> 5, idx & 31, total);
           }
         }
-        bar_sync(1, kDqThreads);  // the flag word is reused by the next partial segment
       }
       if (threadIdx.x == 0 && first_seg) TC_TRACE(13);
       first_seg = false;
@@ -929,13 +927,13 @@ __global__ void __launch_bounds__(Cfg<MB, XRES>::kThreads, Cfg<MB, XRES>::kMinBl
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+std::atomic<unsigned> g_launch_seq{0};  // launch tag of the split fix-up (one counter for ALL instantiations)
 int g_ctas_per_sm = 0;  // 0 = heuristic (tuning: env TG_TC_CTAS)
 int g_split = -1;       // -1 = heuristic, 0 = whole row blocks per CTA, 1 = stream-K over stages (tuning: env TG_TC_SPLIT)
 
 struct DeviceInfo {
   int n_sm = 0;
-  float* ws_partial = nullptr;
-  unsigned* ws_counter = nullptr;
+  unsigned long long* ws_partial = nullptr;
 };
 static int device_info(DeviceInfo** out) {
   static thread_local DeviceInfo info[kMaxDevices];
@@ -945,8 +943,7 @@ static int device_info(DeviceInfo** out) {
     cudaGetDevice(&dev);
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    if (cudaGetSymbolAddress((void**)&d.ws_partial, g_ws_partial) != cudaSuccess ||
-        cudaGetSymbolAddress((void**)&d.ws_counter, g_ws_counter) != cudaSuccess) {
+    if (cudaGetSymbolAddress((void**)&d.ws_partial, g_ws_partial) != cudaSuccess) {
       set_error("cudaGetSymbolAddress failed: %s", cudaGetErrorString(cudaGetLastError()));
       return TG_ERR_CUDA;
     }
@@ -1015,10 +1012,9 @@ int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) 
     p.cq = (int)(row_blocks / G);
     p.cr = (int)(row_blocks % G);
   }
-  static std::atomic<unsigned> pool{0};
-  const unsigned pl = pool.fetch_add(1u, std::memory_order_relaxed) % kWsPools;
-  p.ws_partial = di->ws_partial + (size_t)pl * (kMaxGrid * 2 * 16 * 32);
-  p.ws_counter = di->ws_counter + (size_t)pl * kMaxGrid;
+  const unsigned seq = g_launch_seq.fetch_add(1u, std::memory_order_relaxed) + 1u;  // process-wide: tags must be unique
+  p.ws_partial = di->ws_partial + (size_t)(seq % kWsPools) * (kMaxGrid * 2 * 16 * 32);
+  p.ws_tag = seq;
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)G, 1, 1);
