@@ -20,13 +20,9 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches += (uint64_t)n; }
 
 void set_w4_options(int pdl, int static_weights);
-int launch_gemm_w4_frag_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut, const uint8_t* exps,
-                          int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik, tg_w4_format fmt, tg_dtype dt,
-                          const uint16_t* const_lut, cudaStream_t st);
-// activation rows from which the B-layout 4-bit GEMM uses the fragment-order kernel (gemv_w4_frag.cu); 0 = never.
-// Measured at 4096^2 (profiles/r1/frag_kernel_m_sweep.txt): one 8-row pass of it costs ~15.7 us, a 4-row pass of the
-// lane-per-row kernel ~8.7 us, so it wins from 13 rows on (2 passes vs 4).  tg_set_option(TG_OPT_FRAG_MIN_ROWS, v).
-int g_frag_min_rows = 13;
+// B-layout 4-bit GEMM kernel choice (tg_set_option(TG_OPT_W4_KERNEL, v)): 0 = automatic, 1 = always the tcgen05 kernel
+// (gemv_w4_tc.cu), 2 = the lane-per-row mma.sync kernel (gemv_w4_b.cu) wherever it applies (<= 4 activation rows per pass).
+int g_w4_kernel = 0;
 int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
                         const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
                         tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st,
@@ -36,9 +32,17 @@ int launch_gemm_w4_tc_B(void* y, const void* x, const int32_t* w, const void* sz
                         const uint16_t* const_lut, cudaStream_t st, void* const* y_peers = nullptr, int n_peers = 0,
                         int64_t y_row_stride = 0, int silu_pairs = 0);
 void set_tc_ctas_per_sm(int v);
-static bool use_old_b() {
-  static const bool v = getenv("TG_W4_OLD") != nullptr && atoi(getenv("TG_W4_OLD")) != 0;  // A/B switch while the tcgen05 kernel is tuned
-  return v;
+// Automatic choice, from measurements on a B200 (profiles/r2/kernel_choice.md): the tcgen05 kernel handles 16 rows per
+// pass and wins wherever a CTA has more than a handful of ring stages to amortise its prologue; for a decode GEMV so
+// small that every SM gets at most one 32-row block of <= 4096 k (4096 x 4096: 64 KB per SM), the mma.sync kernel's 16
+// consumer warps per CTA finish the block faster than the tcgen05 kernel's 8 dequant warps.
+static bool use_mma_sync_b(int64_t rows_x, int64_t w_rows, int64_t k) {
+  static const int env = getenv("TG_W4_KERNEL") ? atoi(getenv("TG_W4_KERNEL")) : 0;  // tuning override
+  const int mode = env ? env : g_w4_kernel;
+  if (mode == 1) return false;
+  if (rows_x > 4) return false;
+  if (mode == 2) return true;
+  return rows_x == 1 && k <= 4096 && div_up(w_rows, 32) <= 148;
 }
 int launch_gemm_w4_rm_A(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
                         const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
@@ -47,45 +51,29 @@ int launch_gemm_w4_rm_A(void* y, const void* x, const int32_t* w, const void* sz
 namespace {
 
 // int4 and mx4 run through the LUT kernels with a constant table per dtype
-// (reference: Dequantization.cuh:136-260 "code - 8", FloatDefs.cuh:18-34 kMX4_Values)
-__device__ __align__(16) uint16_t g_const_luts[4][16];  // [int4 bf16, int4 fp16, mx4 bf16, mx4 fp16]
+// (reference: Dequantization.cuh:136-260 "code - 8", FloatDefs.cuh:18-34 kMX4_Values).  Compile-time bit patterns:
+// no init kernel, no stream ordering to worry about, usable inside CUDA graph capture from the first call on.
+__device__ __align__(16) const uint16_t g_const_luts[4][16] = {
+    // int4, bf16: -8 .. 7
+    {0xC100, 0xC0E0, 0xC0C0, 0xC0A0, 0xC080, 0xC040, 0xC000, 0xBF80, 0x0000, 0x3F80, 0x4000, 0x4040, 0x4080, 0x40A0, 0x40C0, 0x40E0},
+    // int4, fp16: -8 .. 7
+    {0xC800, 0xC700, 0xC600, 0xC500, 0xC400, 0xC200, 0xC000, 0xBC00, 0x0000, 0x3C00, 0x4000, 0x4200, 0x4400, 0x4500, 0x4600, 0x4700},
+    // mx4 (fp4 e2m1), bf16: 0, .5, 1, 1.5, 2, 3, 4, 6, -0, ...
+    {0x0000, 0x3F00, 0x3F80, 0x3FC0, 0x4000, 0x4040, 0x4080, 0x40C0, 0x8000, 0xBF00, 0xBF80, 0xBFC0, 0xC000, 0xC040, 0xC080, 0xC0C0},
+    // mx4, fp16
+    {0x0000, 0x3800, 0x3C00, 0x3E00, 0x4000, 0x4200, 0x4400, 0x4600, 0x8000, 0xB800, 0xBC00, 0xBE00, 0xC000, 0xC200, 0xC400, 0xC600},
+};
 
-__global__ void init_const_luts_kernel() {
-  const int i = threadIdx.x;
-  if (i < 16) {
-    const float mx[16] = {0.f, .5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f, -0.f, -.5f, -1.f, -1.5f, -2.f, -3.f, -4.f, -6.f};
-    g_const_luts[0][i] = __bfloat16_as_ushort(__float2bfloat16_rn((float)(i - 8)));
-    g_const_luts[1][i] = __half_as_ushort(__float2half_rn((float)(i - 8)));
-    g_const_luts[2][i] = __bfloat16_as_ushort(__float2bfloat16_rn(mx[i]));
-    g_const_luts[3][i] = __half_as_ushort(__float2half_rn(mx[i]));
-  }
-}
-
-// Returns the device address of the constant LUT for (fmt, dt); on first use per
-// (thread, device) the table is filled by a 1-warp kernel ordered on the caller's stream.
-int const_lut_for(tg_w4_format fmt, tg_dtype dt, cudaStream_t st, const uint16_t** out) {
-  constexpr int kMaxDev = 64;
-  static thread_local const uint16_t* base[kMaxDev] = {nullptr};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) {
-    set_error("no usable CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
-    return TG_ERR_CUDA;
-  }
+// device address of the constant LUT for (fmt, dt) on the current device
+int const_lut_for(tg_w4_format fmt, tg_dtype dt, cudaStream_t, const uint16_t** out) {
+  static thread_local const uint16_t* base[kMaxDevices] = {nullptr};
+  const int dev = current_device_slot();
   if (base[dev] == nullptr) {
-    uint16_t* p = nullptr;
+    const uint16_t* p = nullptr;
     if (cudaGetSymbolAddress((void**)&p, g_const_luts) != cudaSuccess) {
       set_error("cudaGetSymbolAddress failed: %s", cudaGetErrorString(cudaGetLastError()));
       return TG_ERR_CUDA;
     }
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    (void)cudaStreamIsCapturing(st, &cap);
-    if (cap != cudaStreamCaptureStatusNone) {
-      // filling the table inside a capture would bake a one-off init into the graph
-      set_error("first int4/mx4 call on this device must happen outside CUDA graph capture");
-      return TG_ERR_UNSUPPORTED;
-    }
-    init_const_luts_kernel<<<1, 32, 0, st>>>();
-    TG_CHECK_LAUNCH("init_const_luts");
     base[dev] = p;
   }
   *out = base[dev] + ((fmt == TG_W4_MX4 ? 2 : 0) + (dt == TG_FP16 ? 1 : 0)) * 16;
@@ -127,9 +115,9 @@ int tg_set_option(tg_option option, int value) {
   switch (option) {
     case TG_OPT_PDL: set_w4_options(value != 0, -1); return TG_OK;
     case TG_OPT_STATIC_WEIGHTS: set_w4_options(-1, value != 0); return TG_OK;
-    case TG_OPT_FRAG_MIN_ROWS:
-      if (value < 0) break;
-      g_frag_min_rows = value;
+    case TG_OPT_W4_KERNEL:
+      if (value < 0 || value > 2) break;
+      g_w4_kernel = value;
       return TG_OK;
   }
   set_error("tg_set_option: unknown option %d", (int)option);
@@ -170,17 +158,11 @@ int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_z
     rc = const_lut_for(format, dtype, (cudaStream_t)stream, &clut);
     if (rc != TG_OK) return rc;
   }
-  if (side == TG_WEIGHT_B && !use_old_b())
-    return launch_gemm_w4_tc_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
-                               (cudaStream_t)stream);
   if (side == TG_WEIGHT_B) {
-    // more activation rows than the decode kernel carries per pass: fragment-order tensor-core kernel (gemv_w4_frag.cu)
-    if (g_frag_min_rows > 0 && rows_x >= g_frag_min_rows) {
-      rc = launch_gemm_w4_frag_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
+    if (use_mma_sync_b(rows_x, w_rows, k))
+      return launch_gemm_w4_rm_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
                                  (cudaStream_t)stream);
-      if (rc != -1) return rc;  // -1: shape not handled there (k too long to stage the activations)
-    }
-    return launch_gemm_w4_rm_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
+    return launch_gemm_w4_tc_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
                                (cudaStream_t)stream);
   }
   return launch_gemm_w4_rm_A(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
@@ -217,7 +199,7 @@ int tg_gemm_w4_rm_sharded(void* const* y_peers, int n_peers, int64_t y_row_strid
     rc = const_lut_for(format, dtype, (cudaStream_t)stream, &clut);
     if (rc != TG_OK) return rc;
   }
-  if (!use_old_b())
+  if (!use_mma_sync_b(rows_x, w_rows, k))
     return launch_gemm_w4_tc_B(y_peers[0], x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
                                clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride);
   return launch_gemm_w4_rm_B(y_peers[0], x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
@@ -249,7 +231,7 @@ int tg_gemm_w4_rm_silu_pairs(void* y, const void* x, const int32_t* w, const voi
     rc = const_lut_for(format, dtype, (cudaStream_t)stream, &clut);
     if (rc != TG_OK) return rc;
   }
-  if (!use_old_b())
+  if (!use_mma_sync_b(rows_x, w_rows, k))
     return launch_gemm_w4_tc_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
                                (cudaStream_t)stream, nullptr, 0, 0, /*silu_pairs=*/1);
   return launch_gemm_w4_rm_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,

@@ -431,7 +431,8 @@ int launch_a(const Params& p0, int row_blocks, int64_t rows_x, const uint16_t* x
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
   }
   Params p = p0;
-  const int slots = n_sm / p.splits > 0 ? n_sm / p.splits : 1;
+  // k split across a cluster: one row block per cluster (the DSMEM exchange after the block loop belongs to ONE block)
+  const int slots = p.splits > 1 ? row_blocks : n_sm;
   const int gx = row_blocks < slots ? row_blocks : slots;
   p.blk_q = row_blocks / gx;
   p.blk_r = row_blocks % gx;

@@ -676,7 +676,8 @@ int launch_one(const Params& p, const Peers& peers, int row_blocks, cudaStream_t
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
   }
   static const bool persist = getenv("TG_W4_PERSIST") == nullptr || atoi(getenv("TG_W4_PERSIST")) != 0;  // tuning knob
-  const int slots = !persist ? row_blocks : (n_sm / p.splits > 0 ? n_sm / p.splits : 1);
+  // k split across a cluster: one row block per cluster (the DSMEM exchange after the block loop belongs to ONE block)
+  const int slots = (!persist || p.splits > 1) ? row_blocks : n_sm;
   const int gx = row_blocks < slots ? row_blocks : slots;
   Params pp = p;
   pp.blk_q = row_blocks / gx;

@@ -1064,7 +1064,10 @@ int launch_m(ParamsTC p, const Peers& peers0, int row_blocks, int64_t rows_x, co
     // the decode kernel (one activation row) is specialised for groups >= 128 (one group word per stage)
     if (res && p.glog2 >= 7) rc = launch_one<DT, IK, 4, true, MX4, true>(p, peers, row_blocks, st);
     else if (res) rc = launch_one<DT, IK, 4, true, MX4, false>(p, peers, row_blocks, st);
-    else if (p.m <= 4) rc = launch_one<DT, IK, 4, false, MX4, false>(p, peers, row_blocks, st);
+    // 2..4 rows: the two-CTAs-per-SM kernel pays off once an SM has enough stages to keep both busy; small problems run
+    // faster as one 8-row CTA per SM (measured: profiles/r2/kernel_choice.md)
+    else if (p.m <= 4 && ((int64_t)row_blocks * p.stages_per_row >= 148 * 10 || peers0.n > 0))
+      rc = launch_one<DT, IK, 4, false, MX4, false>(p, peers, row_blocks, st);
     else if (p.m <= 8) rc = launch_one<DT, IK, 8, false, MX4, false>(p, peers, row_blocks, st);
     else rc = launch_one<DT, IK, 16, false, MX4, false>(p, peers, row_blocks, st);
     if (rc != TG_OK) return rc;

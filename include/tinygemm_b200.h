@@ -60,10 +60,10 @@ typedef enum {
    * convert-then-GEMM sequences such as functional.linear_*(reshape_weight=True)).  With the promise (and PDL)
    * the weight stream starts before the previous kernel has finished.  Default 0. */
   TG_OPT_STATIC_WEIGHTS = 1,
-  /* B-layout 4-bit GEMM: number of activation rows from which the fragment-order tensor-core kernel (8 rows per
-   * pass) replaces the lane-per-row decode kernel (4 rows per pass); 0 = never.  Default 13.  Both kernels produce
-   * the same dequantised weights and exact products; only the order of the fp32 partial sums differs. */
-  TG_OPT_FRAG_MIN_ROWS = 2
+  /* B-layout 4-bit GEMM kernel choice: 0 = automatic (default), 1 = always the tcgen05 / TMEM kernel (one pass for up
+   * to 16 activation rows), 2 = the lane-per-row mma.sync decode kernel wherever it applies (<= 4 rows per pass).  All
+   * of them produce the same dequantised weights and exact products; only the order of the fp32 partial sums differs. */
+  TG_OPT_W4_KERNEL = 2
 } tg_option;
 int tg_set_option(tg_option option, int value);
 

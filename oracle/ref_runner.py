@@ -4,6 +4,7 @@ TEST INFRASTRUCTURE ONLY.  Must be its own process: the reference registers the 
 `torch.ops.tinygemm` namespace as this repo's library.
 
   python oracle/ref_runner.py golden <out.npz>      evaluate every parity case (oracle/cases.py)
+  python oracle/ref_runner.py golden_big <out.npz>  the headline-size cases (oracle/big_cases.py), sampled columns
   python oracle/ref_runner.py bench <n> <k> <iters> time the reference any4 GEMV (rotating copies)
   python oracle/ref_runner.py sweep                 the format x m sweep of bench.py (4096^2) on the reference kernels
 """
@@ -44,6 +45,23 @@ def golden(out_path):
             else:
                 out[name] = t.numpy()
     torch.cuda.synchronize()
+    np.savez_compressed(out_path, **out)
+    print(f"[ref] wrote {out_path}: {len(out)} arrays")
+
+
+def golden_big(out_path):
+    """The headline-size cases (oracle/big_cases.py): sampled output columns of the reference kernels."""
+    from oracle import big_cases as B
+
+    load_reference()
+    out = {}
+    for c in B.cases():
+        try:
+            y = B.run_ops(c, "cuda:0")
+        except RuntimeError as e:
+            print(f"[ref] {B.case_id(c)} rejected by the reference: {str(e).splitlines()[0][:120]}")
+            continue
+        out[B.case_id(c)] = B.to_u16(y)
     np.savez_compressed(out_path, **out)
     print(f"[ref] wrote {out_path}: {len(out)} arrays")
 
@@ -156,5 +174,7 @@ if __name__ == "__main__":
         sweep()
     elif sys.argv[1] == "golden":
         golden(sys.argv[2])
+    elif sys.argv[1] == "golden_big":
+        golden_big(sys.argv[2])
     elif sys.argv[1] == "bench":
         bench(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))

@@ -97,9 +97,9 @@ def test_argument_checks():
 
 @pytest.mark.parametrize("rows", [(4096, 1024, 1024), (512, 256), (6144, 4096)])
 def test_fuse_rows(rows):
-    """One launch over concatenated rows computes every row exactly as the separate layers do.  The results are
-    bit-identical whenever the launches use the same k-split (the split only changes the order of the fp32 partial
-    sums); small layers that get a cluster split on their own (1024 x 4096) may differ in the last bf16 bit."""
+    """One launch over concatenated rows computes every row as the separate layers do: same dequantised weights, same
+    exact products; the kernel choice and the stream-K split depend on the launch size, so the ORDER of the fp32
+    partial sums (and with it the last bf16 bit of a few outputs) may differ."""
     from any4_b200.modules import Any4Linear, fuse_rows
     from bench import G, synth_layer
 
@@ -113,15 +113,11 @@ def test_fuse_rows(rows):
         lin.weight_reshaped = True
         lins.append(lin)
     fused = fuse_rows(lins)
-    same_split = all(n >= 4096 for n in rows) or all(n < 1184 for n in rows + (sum(rows),))
     for m in (1, 3):
         x = torch.randn(m, k, device=dev).bfloat16()
         got, want = fused(x), torch.cat([lin(x) for lin in lins], -1)
-        if same_split:
-            assert torch.equal(got, want)
-        else:
-            assert ((got.float() - want.float()).abs() <= 2.0 ** -7 * want.float().abs() + 1e-6).all()
-            assert (got == want).float().mean() > 0.98
+        assert ((got.float() - want.float()).abs() <= 2.0 ** -7 * want.float().abs() + 1e-6).all()
+        assert (got == want).float().mean() > 0.98
 
 
 @pytest.mark.parametrize("m", [1, 3])
@@ -150,8 +146,9 @@ def test_linear_silu_pairs(m, n, k):
     yg, yu = lins[0](x), lins[1](x)
     want = TF.silu(yg) * yu
     plain = fused(x).view(m, n, 2)                                 # the interleaved weight through the plain GEMV
-    if n >= 2400:                                                  # same k-split as the separate layers: bit-exact
-        assert torch.equal(plain[..., 0], yg) and torch.equal(plain[..., 1], yu)
+    for a, b in ((plain[..., 0], yg), (plain[..., 1], yu)):        # same weights, possibly another summation order
+        assert ((a.float() - b.float()).abs() <= 2.0 ** -7 * b.float().abs() + 1e-6).all()
+        assert (a == b).float().mean() > 0.98
     got = D.linear_silu_pairs(fused, x)
     assert got.shape == (m, n)
     assert ((got.float() - want.float()).abs() <= 2.0 ** -6 * want.float().abs() + 1e-6).all()

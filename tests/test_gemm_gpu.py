@@ -176,10 +176,10 @@ def test_large_shape_linearity_and_rows(cuda_device):
 
 
 @pytest.mark.parametrize("fmt", ["any4r", "int4", "mx4"])
-@pytest.mark.parametrize("m", [3, 8, 16])
-def test_fragment_kernel_agrees_with_decode_kernel(fmt, m):
-    """B-layout 4-bit GEMM: the fragment-order kernel (TG_OPT_FRAG_MIN_ROWS, default from 13 rows) and the
-    lane-per-row kernel dequantise identically and differ only in the order of the fp32 partial sums."""
+@pytest.mark.parametrize("m", [1, 3, 4])
+def test_tcgen05_kernel_agrees_with_mma_sync_kernel(fmt, m):
+    """B-layout 4-bit GEMM: the tcgen05 / TMEM kernel (TG_OPT_W4_KERNEL = 1) and the lane-per-row mma.sync kernel
+    (= 2) dequantise identically and differ only in the order of the fp32 partial sums."""
     import tinygemm  # noqa: F401
     from any4_b200 import _native
     from any4_b200 import utils as U
@@ -203,12 +203,12 @@ def test_fragment_kernel_agrees_with_decode_kernel(fmt, m):
             lut = (torch.rand(n, 16, device=dev, generator=gen) * 15).sort(1).values.bfloat16() - 8
             run = lambda: ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(x, w, g, sz, lut, True)
     try:
-        assert lib.tg_set_option(2, 0) == 0          # never the fragment kernel
+        assert lib.tg_set_option(2, 2) == 0          # mma.sync kernel
         ref = run()
-        assert lib.tg_set_option(2, 1) == 0          # always
+        assert lib.tg_set_option(2, 1) == 0          # tcgen05 kernel
         got = run()
     finally:
-        lib.tg_set_option(2, 13)
+        lib.tg_set_option(2, 0)
     assert got.shape == ref.shape
     assert ((got.float() - ref.float()).abs() <= 2.0 ** -7 * ref.float().abs() + 1e-3).all()
     assert (got == ref).float().mean() > 0.9
