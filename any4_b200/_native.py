@@ -17,12 +17,12 @@ OPS_PATH = os.path.join(LIB_DIR, "tinygemm_ops.so")
 _capi = None
 _ops_loaded = False
 
-# every symbol include/tinygemm_b200.h declares (checked by tests/test_capi_symbols.py)
+# every symbol include/tinygemm_b200.h declares (checked by tests/test_capi_cpu.py)
 CAPI_SYMBOLS = (
     "tg_set_option", "tg_last_error", "tg_version", "tg_launch_count", "tg_reset_launch_count",
     "tg_convert_to_A", "tg_convert_from_A", "tg_convert_to_B", "tg_convert_from_B",
     "tg_convert_to_Aint4", "tg_convert_to_Aint8", "tg_convert_to_Bint4", "tg_convert_to_Bint8",
-    "tg_gemm_w4_rm", "tg_gemm_w4_rm_sharded", "tg_gemm_w8_rm", "tg_gemm_w16_rm",
+    "tg_gemm_w4_rm", "tg_gemm_w4_rm_sharded", "tg_gemm_w4_rm_exchange", "tg_gemm_w8_rm", "tg_gemm_w16_rm",
     "tg_gemm_tc_workspace_bytes", "tg_gemm_w4_tc", "tg_gemm_w8_tc", "tg_gemm_w16_tc",
     "tg_dequant_int4",
     "tg_decode_add_rmsnorm", "tg_decode_silu_mul", "tg_decode_rope_attention", "tg_gemm_w4_rm_silu_pairs",
@@ -60,6 +60,9 @@ def capi():
     lib.tg_gemm_w4_rm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, i32, vp]
     if hasattr(lib, "tg_gemm_w4_rm_sharded"):  # (absent only in older builds loaded through ANY4_B200_LIB_DIR)
         lib.tg_gemm_w4_rm_sharded.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
+    if hasattr(lib, "tg_gemm_w4_rm_exchange"):
+        u32 = ctypes.c_uint32
+        lib.tg_gemm_w4_rm_exchange.argtypes = [vp, vp, i32, u32, i32, i64, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
     lib.tg_gemm_w8_rm.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
     lib.tg_gemm_w16_rm.argtypes = [vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
     lib.tg_gemm_tc_workspace_bytes.argtypes = [i64, i64, i64]
@@ -91,13 +94,6 @@ def load_ops():
         return
     import torch
 
-    other = os.environ.get("ANY4_B200_OPS_LIB")
-    if other:
-        # benchmarking aid (bench_llama.py --impl reference): register ANOTHER implementation of the same 19
-        # `tinygemm::` schemas - the unmodified reference extension - under this package's Python layer
-        torch.ops.load_library(other)
-        _ops_loaded = True
-        return
     if not os.path.exists(OPS_PATH):
         raise _missing(OPS_PATH)
     capi()  # make sure the dependency is resolvable even without the rpath

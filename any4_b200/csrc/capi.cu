@@ -30,7 +30,8 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
 int launch_gemm_w4_tc_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut, const uint8_t* exps,
                         int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik, tg_w4_format fmt, tg_dtype dt,
                         const uint16_t* const_lut, cudaStream_t st, void* const* y_peers = nullptr, int n_peers = 0,
-                        int64_t y_row_stride = 0, int silu_pairs = 0);
+                        int64_t y_row_stride = 0, int silu_pairs = 0, void* const* flag_peers = nullptr, int self_rank = 0,
+                        uint32_t flag_target = 0);
 void set_tc_ctas_per_sm(int v);
 // Automatic choice, from measurements on a B200 (profiles/r2/kernel_choice.md): the tcgen05 kernel handles 16 rows per
 // pass and wins wherever a CTA has more than a handful of ring stages to amortise its prologue; for a decode GEMV so
@@ -169,13 +170,17 @@ int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_z
                              (cudaStream_t)stream);
 }
 
-int tg_gemm_w4_rm_sharded(void* const* y_peers, int n_peers, int64_t y_row_stride, const void* x, const int32_t* w,
-                          const void* scales_zeros, const void* lut, const uint8_t* exponents, int64_t rows_x,
-                          int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_w4_format format, tg_dtype dtype,
-                          void* stream) {
-  const char* fn = "tg_gemm_w4_rm_sharded";
+static int gemm_w4_rm_sharded_impl(const char* fn, void* const* y_peers, void* const* flag_peers, int self_rank,
+                                   uint32_t flag_target, int n_peers, int64_t y_row_stride, const void* x, const int32_t* w,
+                                   const void* scales_zeros, const void* lut, const uint8_t* exponents, int64_t rows_x,
+                                   int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_w4_format format,
+                                   tg_dtype dtype, void* stream) {
   TG_REQUIRE(y_peers != nullptr && n_peers >= 1 && n_peers <= 8, "%s: 1..8 peer output pointers are required", fn);
   for (int r = 0; r < n_peers; ++r) TG_REQUIRE(y_peers[r] != nullptr, "%s: null peer pointer %d", fn, r);
+  if (flag_peers != nullptr) {
+    TG_REQUIRE(self_rank >= 0 && self_rank < n_peers, "%s: bad self_rank %d", fn, self_rank);
+    for (int r = 0; r < n_peers; ++r) TG_REQUIRE(flag_peers[r] != nullptr, "%s: null flag pointer %d", fn, r);
+  }
   TG_REQUIRE(y_row_stride >= w_rows, "%s: output row stride (%lld) smaller than the shard (%lld)", fn,
              (long long)y_row_stride, (long long)w_rows);
   int rc = check_common(fn, y_peers[0], x, w, rows_x, w_rows, k, TG_WEIGHT_B, dtype);
@@ -199,11 +204,32 @@ int tg_gemm_w4_rm_sharded(void* const* y_peers, int n_peers, int64_t y_row_strid
     rc = const_lut_for(format, dtype, (cudaStream_t)stream, &clut);
     if (rc != TG_OK) return rc;
   }
-  if (!use_mma_sync_b(rows_x, w_rows, k))
+  // the peer-store epilogue lives in the tcgen05 kernel (the in-kernel completion needs it; the mma.sync kernel keeps
+  // a plain peer-store variant for TG_OPT_W4_KERNEL = 2)
+  if (flag_peers != nullptr || !use_mma_sync_b(rows_x, w_rows, k))
     return launch_gemm_w4_tc_B(y_peers[0], x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
-                               clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride);
+                               clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride, 0, flag_peers, self_rank,
+                               flag_target);
   return launch_gemm_w4_rm_B(y_peers[0], x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
                              clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride);
+}
+
+int tg_gemm_w4_rm_sharded(void* const* y_peers, int n_peers, int64_t y_row_stride, const void* x, const int32_t* w,
+                          const void* scales_zeros, const void* lut, const uint8_t* exponents, int64_t rows_x,
+                          int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_w4_format format, tg_dtype dtype,
+                          void* stream) {
+  return gemm_w4_rm_sharded_impl("tg_gemm_w4_rm_sharded", y_peers, nullptr, 0, 0, n_peers, y_row_stride, x, w, scales_zeros,
+                                 lut, exponents, rows_x, w_rows, k, group, inner_k_tiles, format, dtype, stream);
+}
+
+int tg_gemm_w4_rm_exchange(void* const* y_peers, void* const* flag_peers, int self_rank, uint32_t flag_target, int n_peers,
+                           int64_t y_row_stride, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
+                           const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
+                           int inner_k_tiles, tg_w4_format format, tg_dtype dtype, void* stream) {
+  const char* fn = "tg_gemm_w4_rm_exchange";
+  TG_REQUIRE(flag_peers != nullptr, "%s: flag pointers are required", fn);
+  return gemm_w4_rm_sharded_impl(fn, y_peers, flag_peers, self_rank, flag_target, n_peers, y_row_stride, x, w, scales_zeros,
+                                 lut, exponents, rows_x, w_rows, k, group, inner_k_tiles, format, dtype, stream);
 }
 
 int tg_gemm_w4_rm_silu_pairs(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,

@@ -66,6 +66,7 @@ constexpr int kWsPools = 4;
 
 // split fix-up workspace: tagged fp32 partial sums [pool][CTA][slot 0/1][mi][row], one 8-byte word (value, launch tag) each
 __device__ unsigned long long g_ws_partial[kWsPools][kMaxGrid * 2 * 16 * 32];
+__device__ unsigned g_ws_done[kWsPools];  // CTAs of a launch that have finished (row-sharded exchange, self-resetting)
 
 struct ParamsTC {
   const uint8_t* w;      // packed weight
@@ -76,6 +77,7 @@ struct ParamsTC {
   const uint16_t* lut;   // [16] or [w_rows][16]
   unsigned long long* ws_partial;  // this launch's workspace pool
   uint32_t ws_tag;                  // launch tag carried by every partial of this launch
+  unsigned* ws_done;                // finished-CTA counter of this launch (row-sharded exchange only)
   int64_t tile_stride;   // bytes between consecutive n-tiles of the packed weight = 4 * k
   int64_t y_stride;
   int lut_stride;        // 0 or 16
@@ -780,6 +782,26 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       first_seg = false;
     }
     if (threadIdx.x == 0) TC_TRACE(14);
+    if constexpr (PEERS) {
+      if (peers.my_flag != nullptr) {
+        // in-kernel completion of the exchange (see w4::Peers)
+        bar_sync(1, kDqThreads);  // every peer store of this CTA has been issued
+        if (threadIdx.x == 0) {
+          __threadfence_system();  // ... and is visible system-wide
+          const unsigned done = atomicAdd(p.ws_done, 1u);
+          if (done == gridDim.x - 1u) {  // the launch's last CTA signals for the whole rank
+            *p.ws_done = 0u;
+            __threadfence_system();
+            for (int r = 0; r < peers.n; ++r)
+              asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(peers.flag[r]) : "memory");
+            uint32_t v;
+            do {
+              asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(peers.my_flag) : "memory");
+            } while ((int32_t)(v - peers.target) < 0);
+          }
+        }
+      }
+    }
   } else if (warp == kDqWarps) {
     // =============================================================== TMA producer: the rest of the stream
     while (pc.u < u_end) {
@@ -934,6 +956,7 @@ int g_split = -1;       // -1 = heuristic, 0 = whole row blocks per CTA, 1 = str
 struct DeviceInfo {
   int n_sm = 0;
   unsigned long long* ws_partial = nullptr;
+  unsigned* ws_done = nullptr;
 };
 static int device_info(DeviceInfo** out) {
   static thread_local DeviceInfo info[kMaxDevices];
@@ -943,7 +966,8 @@ static int device_info(DeviceInfo** out) {
     cudaGetDevice(&dev);
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    if (cudaGetSymbolAddress((void**)&d.ws_partial, g_ws_partial) != cudaSuccess) {
+    if (cudaGetSymbolAddress((void**)&d.ws_partial, g_ws_partial) != cudaSuccess ||
+        cudaGetSymbolAddress((void**)&d.ws_done, g_ws_done) != cudaSuccess) {
       set_error("cudaGetSymbolAddress failed: %s", cudaGetErrorString(cudaGetLastError()));
       return TG_ERR_CUDA;
     }
@@ -1015,6 +1039,7 @@ int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) 
   const unsigned seq = g_launch_seq.fetch_add(1u, std::memory_order_relaxed) + 1u;  // process-wide: tags must be unique
   p.ws_partial = di->ws_partial + (size_t)(seq % kWsPools) * (kMaxGrid * 2 * 16 * 32);
   p.ws_tag = seq;
+  p.ws_done = di->ws_done + (seq % kWsPools);
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)G, 1, 1);
@@ -1092,11 +1117,16 @@ int launch_ik(const ParamsTC& p, const Peers& peers, int ik, int row_blocks, int
 int launch_gemm_w4_tc_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut, const uint8_t* exps,
                         int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik, tg_w4_format fmt, tg_dtype dt,
                         const uint16_t* const_lut, cudaStream_t st, void* const* y_peers, int n_peers, int64_t y_row_stride,
-                        int silu_pairs) {
+                        int silu_pairs, void* const* flag_peers, int self_rank, uint32_t flag_target) {
   tc::ParamsTC p{};
   w4::Peers peers{};
   peers.n = n_peers;
   for (int r = 0; r < n_peers; ++r) peers.y[r] = static_cast<uint16_t*>(y_peers[r]);
+  if (flag_peers != nullptr) {
+    for (int r = 0; r < n_peers; ++r) peers.flag[r] = static_cast<uint32_t*>(flag_peers[r]);
+    peers.my_flag = peers.flag[self_rank];
+    peers.target = flag_target;
+  }
   p.w = reinterpret_cast<const uint8_t*>(w);
   p.sz = (fmt == TG_W4_MX4) ? nullptr : reinterpret_cast<const uint32_t*>(sz);
   p.exps = (fmt == TG_W4_MX4) ? exps : nullptr;

@@ -154,6 +154,13 @@ __device__ __forceinline__ void l2_prefetch_line(const void* src) {
 // outputs to all of them over NVLink (peer pointers are ordinary UVA addresses).
 struct Peers {
   uint16_t* y[8];
+  // optional in-kernel completion of the exchange (tg_gemm_w4_rm_exchange): flag[r] = rank r's copy of a counter in
+  // symmetric memory.  The last CTA of the launch adds 1 to every rank's counter once all of this rank's stores are
+  // system-visible, then waits until its own copy reaches `target` (= every rank has done the same): when the kernel
+  // completes, all ranks' shards have landed in this rank's buffer - no barrier kernel, the PDL chain stays intact.
+  uint32_t* flag[8];
+  uint32_t* my_flag;
+  uint32_t target;
   int n;
 };
 template <bool PEERS>

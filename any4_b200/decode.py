@@ -26,32 +26,50 @@ def _check(rc):
         raise RuntimeError(_native.last_error())
 
 
-def _req(t, name):
+def _req(t, name, like=None):
     if not (t.is_cuda and t.is_contiguous() and t.dtype in _DT):
         raise RuntimeError(f"{name} must be a contiguous CUDA bf16/fp16 tensor")
+    if like is not None and (t.device != like.device or t.dtype != like.dtype):
+        raise RuntimeError(f"{name} must live on {like.device} with dtype {like.dtype}")
+
+
+def _one_token(t, name):
+    if t.dim() > 1 and t.numel() != t.shape[-1]:
+        raise RuntimeError(f"{name}: the decode ops take ONE token ({tuple(t.shape)} has more than one row)")
+
+
+def _out(out, shape, like, name="out"):
+    if out is None:
+        return torch.empty(shape, device=like.device, dtype=like.dtype)
+    _req(out, name, like)
+    if tuple(out.shape) != tuple(shape):
+        raise RuntimeError(f"{name} must have shape {tuple(shape)}")
+    return out
 
 
 def add_rmsnorm(h, delta, weight, eps, out=None):
     """h += delta (in place, rounded; delta may be None); returns rmsnorm(h, eps) * weight."""
-    _req(h, "h"), _req(weight, "weight")
+    _req(h, "h"), _req(weight, "weight", h), _one_token(h, "h")
     if delta is not None:
-        _req(delta, "delta")
-        if delta.numel() != h.numel() or delta.dtype != h.dtype:
+        _req(delta, "delta", h)
+        if delta.numel() != h.numel():
             raise RuntimeError("delta must match h")
-    if weight.numel() != h.numel() or weight.dtype != h.dtype:
+    if weight.numel() != h.numel():
         raise RuntimeError("weight must match h")
-    out = torch.empty_like(h) if out is None else out
-    _check(_native.capi().tg_decode_add_rmsnorm(_p(h), _p(delta), _p(weight), _p(out), h.numel(), float(eps),
-                                                _DT[h.dtype], _stream()))
+    out = _out(out, h.shape, h)
+    with torch.cuda.device(h.device):
+        _check(_native.capi().tg_decode_add_rmsnorm(_p(h), _p(delta), _p(weight), _p(out), h.numel(), float(eps),
+                                                    _DT[h.dtype], _stream()))
     return out
 
 
 def silu_mul(gate_up, out=None):
     """gate_up = [gate | up] (2n values, e.g. the output of a fused gate/up GEMV) -> silu(gate) * up, n values."""
-    _req(gate_up, "gate_up")
+    _req(gate_up, "gate_up"), _one_token(gate_up, "gate_up")
     n = gate_up.numel() // 2
-    out = torch.empty(gate_up.shape[:-1] + (n,), device=gate_up.device, dtype=gate_up.dtype) if out is None else out
-    _check(_native.capi().tg_decode_silu_mul(_p(gate_up), _p(out), n, _DT[gate_up.dtype], _stream()))
+    out = _out(out, gate_up.shape[:-1] + (n,), gate_up)
+    with torch.cuda.device(gate_up.device):
+        _check(_native.capi().tg_decode_silu_mul(_p(gate_up), _p(out), n, _DT[gate_up.dtype], _stream()))
     return out
 
 
@@ -59,7 +77,8 @@ def rope_attention(qkv, cos, sin, k_cache, v_cache, pos, n_heads, n_kv_heads, he
     """qkv = [q | k | v] of ONE token: rotary embedding of q and k, append k, v at `pos` to the caches
     [n_kv_heads][cache_len][head_dim], attention over positions 0..pos -> [n_heads * head_dim]."""
     for t, nm in ((qkv, "qkv"), (cos, "cos"), (sin, "sin"), (k_cache, "k_cache"), (v_cache, "v_cache")):
-        _req(t, nm)
+        _req(t, nm, qkv)
+    _one_token(qkv, "qkv")
     if qkv.numel() != (n_heads + 2 * n_kv_heads) * head_dim:
         raise RuntimeError("qkv has the wrong size")
     if cos.numel() != head_dim or sin.numel() != head_dim:
@@ -68,10 +87,11 @@ def rope_attention(qkv, cos, sin, k_cache, v_cache, pos, n_heads, n_kv_heads, he
     if v_cache.numel() != k_cache.numel() or k_cache.numel() != n_kv_heads * cache_len * head_dim:
         raise RuntimeError("k_cache / v_cache must be [n_kv_heads][cache_len][head_dim]")
     scale = head_dim ** -0.5 if scale is None else scale
-    out = torch.empty(qkv.shape[:-1] + (n_heads * head_dim,), device=qkv.device, dtype=qkv.dtype) if out is None else out
-    _check(_native.capi().tg_decode_rope_attention(_p(qkv), _p(cos), _p(sin), _p(k_cache), _p(v_cache), _p(out), n_heads,
-                                                   n_kv_heads, head_dim, int(pos), cache_len, float(scale),
-                                                   _DT[qkv.dtype], _stream()))
+    out = _out(out, qkv.shape[:-1] + (n_heads * head_dim,), qkv)
+    with torch.cuda.device(qkv.device):
+        _check(_native.capi().tg_decode_rope_attention(_p(qkv), _p(cos), _p(sin), _p(k_cache), _p(v_cache), _p(out),
+                                                       n_heads, n_kv_heads, head_dim, int(pos), cache_len, float(scale),
+                                                       _DT[qkv.dtype], _stream()))
     return out
 
 
@@ -85,11 +105,14 @@ def linear_silu_pairs(lin, x):
             and lin.kernel == "linear_y_f16RM_x_f16RM_W_any4TC"):
         raise RuntimeError("linear_silu_pairs needs a packed per-row-LUT Any4Linear with the weight on the right, no bias")
     _req(x, "x")
+    if x.device != lin.weight.device:
+        raise RuntimeError("linear_silu_pairs: x and the layer live on different devices")
     x2 = x.view(-1, x.shape[-1])
     w = lin.weight
     w_rows, ik = w.shape[0] * 8, w.shape[3] * 2
     y = torch.empty(x2.shape[0], w_rows // 2, device=x.device, dtype=x.dtype)
-    _check(_native.capi().tg_gemm_w4_rm_silu_pairs(_p(y), _p(x2), _p(w), _p(lin.scales_and_zeros), _p(lin.lut), None,
-                                                   x2.shape[0], w_rows, x2.shape[1], lin.group_size, ik, 2,
-                                                   _DT[x.dtype], _stream()))
+    with torch.cuda.device(x.device):
+        _check(_native.capi().tg_gemm_w4_rm_silu_pairs(_p(y), _p(x2), _p(w), _p(lin.scales_and_zeros), _p(lin.lut), None,
+                                                       x2.shape[0], w_rows, x2.shape[1], lin.group_size, ik, 2,
+                                                       _DT[x.dtype], _stream()))
     return y.view(*x.shape[:-1], w_rows // 2)

@@ -224,20 +224,33 @@ def _fuse_rows_interleaved(linears):
 
 
 class _SymmWorkspace:
-    """One peer-mapped (symmetric-memory) output workspace per (process group, device): two alternating m x n buffers
-    every rank can store into directly.  Shared by all RowShardedLinear layers of the process."""
+    """One peer-mapped (symmetric-memory) output workspace per (process group, device): a ring of `SLOTS` m x n buffers
+    every rank can store into directly, plus the exchange counter of tg_gemm_w4_rm_exchange.  Shared by all
+    RowShardedLinear layers of the process.
 
+    Contract: the tensor a fused sharded forward returns is a VIEW of ring slot `call % SLOTS`; it stays valid until
+    SLOTS - 1 further fused sharded calls (of any layer) have been issued on this rank.  Consume it (or copy it) before
+    that.  Every rank must issue the same sequence of fused sharded calls."""
+
+    SLOTS = 8
     _cache = {}
 
     def __init__(self, group, device, dtype, m_cap, n_cap):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
 
+        group = group if group is not None else dist.group.WORLD
         self.m_cap, self.n_cap = m_cap, n_cap
-        self.buf = symm.empty((2, m_cap, n_cap), dtype=dtype, device=device)
-        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.buf = symm.empty((self.SLOTS, m_cap, n_cap), dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        self.turn = 0
+        self.flags = symm.empty((16,), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.flag_hdl = symm.rendezvous(self.flags, group)
+        self.flag_ptrs = [int(p) for p in self.flag_hdl.buffer_ptrs]
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's counter is zero before anybody adds to it
+        self.calls = 0
 
     @classmethod
     def get(cls, group, device, dtype, m, n):
@@ -261,11 +274,13 @@ class RowShardedLinear(torch.nn.Module):
     all-reduce: every element is value + 0 + ... + 0, so the result is bit-identical to the
     single-GPU output.
 
-    `fused=True` (B200-native path, weight-on-the-right 4-bit kernels): no collective kernel at all.  The GEMV's
-    epilogue stores this rank's n/R outputs straight into EVERY rank's copy of a symmetric-memory m x n buffer over
-    NVLink (include/tinygemm_b200.h: tg_gemm_w4_rm_sharded); one symmetric-memory barrier on the stream then
-    orders the readers behind all ranks' stores.  Bit-identical to the all-reduce path (same values, no sums).
-    `max_features` sizes the shared workspace (largest out_features of any sharded layer in the process).
+    `fused=True` (B200-native path, weight-on-the-right 4-bit kernels): no collective and no barrier kernel at all.  The
+    GEMV's epilogue stores this rank's n/R outputs straight into EVERY rank's copy of a symmetric-memory m x n buffer
+    over NVLink and completes the exchange itself (include/tinygemm_b200.h: tg_gemm_w4_rm_exchange: a counter in
+    symmetric memory, the kernel's last CTA waits until all ranks' shards have landed).  Bit-identical to the
+    all-reduce path (same values, no sums).  The result is a view of a ring slot of the shared workspace - see
+    _SymmWorkspace for how long it stays valid.  `max_features` sizes the workspace (largest out_features of any
+    sharded layer in the process).
     """
 
     def __init__(self, full: _PackedLinear, rank: int, world: int, group=None, fused: bool = False,
@@ -328,22 +343,28 @@ class RowShardedLinear(torch.nn.Module):
 
         loc = self.local
         m, n = x2d.shape[0], self.out_features
+        if x2d.device != loc.weight.device:
+            raise ValueError("RowShardedLinear: input and weights live on different devices")
         ws = _SymmWorkspace.get(self.group, x2d.device, x2d.dtype, m, self.max_features)
-        turn = ws.turn
-        ws.turn ^= 1
+        slot = ws.calls % ws.SLOTS
+        ws.calls += 1
         elt = x2d.element_size()
-        base = (turn * ws.m_cap * ws.n_cap + self.lo) * elt   # this shard's first column in buffer `turn`
+        base = (slot * ws.m_cap * ws.n_cap + self.lo) * elt   # this shard's first column in ring slot `slot`
         peers = (ctypes.c_void_p * self.world)(*[p + base for p in ws.ptrs])
+        flags = (ctypes.c_void_p * self.world)(*ws.flag_ptrs)
         is_any4 = hasattr(loc, "lut")
         fmt = (2 if loc.lut.dim() == 2 else 1) if is_any4 else 0  # tg_w4_format
         lib = _native.capi()
-        rc = lib.tg_gemm_w4_rm_sharded(
-            peers, self.world, ws.n_cap, ctypes.c_void_p(x2d.data_ptr()), ctypes.c_void_p(loc.weight.data_ptr()),
-            ctypes.c_void_p(loc.scales_and_zeros.data_ptr()),
-            ctypes.c_void_p(loc.lut.data_ptr()) if is_any4 else None, None,
-            m, self.hi - self.lo, x2d.shape[1], loc.group_size, loc.weight.shape[3] * 2, fmt,
-            0 if x2d.dtype == torch.bfloat16 else 1, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(x2d.device):
+            # the exchange completes INSIDE the kernel (its last CTA waits until every rank's shard has landed here):
+            # no barrier / collective launch follows, consumers are ordered by plain stream order
+            rc = lib.tg_gemm_w4_rm_exchange(
+                peers, flags, self.rank, (ws.calls * self.world) & 0xFFFFFFFF, self.world, ws.n_cap,
+                ctypes.c_void_p(x2d.data_ptr()), ctypes.c_void_p(loc.weight.data_ptr()),
+                ctypes.c_void_p(loc.scales_and_zeros.data_ptr()),
+                ctypes.c_void_p(loc.lut.data_ptr()) if is_any4 else None, None,
+                m, self.hi - self.lo, x2d.shape[1], loc.group_size, loc.weight.shape[3] * 2, fmt,
+                0 if x2d.dtype == torch.bfloat16 else 1, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc != 0:
             raise RuntimeError(_native.last_error())
-        ws.hdl.barrier(channel=0)   # all ranks' stores have landed before anyone reads the buffer
-        return ws.buf[turn, :m, :n]
+        return ws.buf[slot, :m, :n]

@@ -132,7 +132,7 @@ class FusedBlock(torch.nn.Module):
 
 
 class Llama(torch.nn.Module):
-    def __init__(self, dev, rank, world, ctx, layers, fused_plumbing):
+    def __init__(self, dev, rank, world, ctx, layers, fused_plumbing, lm_head_any4=False):
         super().__init__()
         gen = torch.Generator(device=dev).manual_seed(7)
         self.fused_plumbing = fused_plumbing
@@ -140,7 +140,15 @@ class Llama(torch.nn.Module):
         blk = FusedBlock if fused_plumbing else Block
         self.blocks = torch.nn.ModuleList([blk(i, dev, rank, world, ctx) for i in range(layers)])
         self.norm = torch.ones(HID, device=dev, dtype=torch.bfloat16)
-        self.lm_head = (torch.randn(VOCAB, HID, device=dev, generator=gen) * 0.02).bfloat16()
+        # lm_head: bf16 on cuBLAS as in the reference (quantize.py:34-36 skips it), or any4 through the same GEMV kernel
+        # (128256 rows, row-sharded like every other layer when world > 1)
+        self.lm_head_any4 = lm_head_any4
+        if lm_head_any4:
+            self.lm_head = make_linear(VOCAB, HID, 777, dev, rank, world, fused=_FUSED)
+            if world > 1:
+                self.lm_head.max_features = max(self.lm_head.max_features, VOCAB)
+        else:
+            self.lm_head = (torch.randn(VOCAB, HID, device=dev, generator=gen) * 0.02).bfloat16()
         pos = torch.tensor([float(ctx)], device=dev)
         inv = 1.0 / (THETA ** (torch.arange(0, HEAD_DIM, 2, device=dev).float() / HEAD_DIM))
         ang = torch.cat([pos[:, None] * inv[None], pos[:, None] * inv[None]], -1)
@@ -155,10 +163,89 @@ class Llama(torch.nn.Module):
             delta = None
             for b in self.blocks:
                 delta = b(h, delta, self.cos1, self.sin1)
-            return F.linear(D.add_rmsnorm(h, delta, self.norm, EPS), self.lm_head)
+            x = D.add_rmsnorm(h, delta, self.norm, EPS)
+            return self.lm_head(x) if self.lm_head_any4 else F.linear(x, self.lm_head)
         for b in self.blocks:
             h = b(h, self.cos, self.sin)
-        return F.linear(F.rms_norm(h, (HID,), self.norm, EPS), self.lm_head)
+        x = F.rms_norm(h, (HID,), self.norm, EPS)
+        return self.lm_head(x) if self.lm_head_any4 else F.linear(x, self.lm_head)
+
+
+def run_decode(dev, rank, world, dist, steps=50, warmup=5, ctx=128, layers=LAYERS, exchange="fused", plumbing="fused",
+               lm_head_any4=False, reference=False, lib=None):
+    """Build the synthetic model, capture one decode step in a CUDA graph, time `steps` replays (max over ranks).
+    Returns the result dict on rank 0 (None elsewhere)."""
+    local = dev.index
+
+    def note(msg):
+        if os.environ.get("LLAMA_DEBUG"):
+            print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    with torch.no_grad():
+        note("building model")
+        global _FUSED
+        _FUSED = exchange == "fused"
+        model = Llama(dev, rank, world, ctx, layers, plumbing == "fused", lm_head_any4)
+        note("model built")
+        tok = torch.tensor([1], device=dev)
+        if lib is not None:
+            lib.tg_reset_launch_count()
+        logits = model(tok)
+        torch.cuda.synchronize()
+        note("first forward done")
+        launches = int(lib.tg_launch_count()) if lib is not None else None
+        assert torch.isfinite(logits.float()).all(), "synthetic model produced non-finite logits"
+        for _ in range(warmup):
+            model(tok)
+        torch.cuda.synchronize()
+        note("warm-up done, capturing")
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = model(tok)
+        note("captured")
+        g.replay()
+        torch.cuda.synchronize()
+        note("first replay done")
+        if dist is not None:
+            dist.barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        clocks = sampler.stop() if sampler else None
+        del g, out, model  # a live CUDA graph holding NCCL kernels keeps destroy_process_group() from returning
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    per_layer = 2 * any4_bytes(HID, HID) + 2 * any4_bytes(KV_HEADS * HEAD_DIM, HID) + 2 * any4_bytes(INTER, HID) + any4_bytes(HID, INTER)
+    quant_bytes = per_layer * layers
+    head_bytes = any4_bytes(VOCAB, HID) / world if lm_head_any4 else VOCAB * HID * 2
+    kv_bytes = layers * 2 * KV_HEADS * (ctx + 1) * HEAD_DIM * 2
+    total = quant_bytes / world + head_bytes + kv_bytes  # per GPU: its shard of the any4 layers, replicated KV (and bf16 head)
+    peak, src = measured_peak()
+    return {
+        "metric": "llama3_8b_any4_g128_decode_tok_per_s", "value": 1e3 / ms, "unit": "tok/s", "n_gpus": world,
+        "impl": "reference tinygemm kernels (recompiled sm_100a) in the same harness" if reference else "any4_b200",
+        "ms_per_token": ms, "steps": steps, "warmup": warmup, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Llama-3-8B any4 g=128 single-token decode, batch 1 (BASELINE configs[2]/[4])",
+                   "layers": layers, "kv_context": ctx, "launch": "one CUDA graph per token",
+                   "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world}, exchange per Linear: {exchange}",
+                   "plumbing": ("q|k|v and gate|up row-fused GEMVs (silu*mul in the gate|up epilogue on 1 GPU) + any4_b200.decode kernels, 7-8 launches / layer"
+                                if plumbing == "fused" else "stock torch ops, 7 GEMV launches / layer"),
+                   "lm_head": "any4 g=128 (row-sharded)" if lm_head_any4 else "bf16 (not quantized, as in the reference)"},
+        "bytes_per_token_per_gpu": total,
+        "roofline": {"bound": "hbm", "achieved": total / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": total / (ms * 1e-3) / 1e9 / peak, "peak_source": src + " (of measured)"},
+        "library_launches_per_token": launches, "clocks": clocks}
 
 
 def main():
@@ -171,6 +258,8 @@ def main():
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--plumbing", default="fused", choices=["fused", "torch"],
                     help="fused: q|k|v and gate|up as one GEMV each + any4_b200.decode kernels; torch: stock ops")
+    ap.add_argument("--lm-head", default="bf16", choices=["bf16", "any4"],
+                    help="bf16: cuBLAS as in the reference (which does not quantize lm_head); any4: through the GEMV kernel")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"],
                     help="reference: the same harness (torch plumbing) on the UNMODIFIED reference tinygemm kernels "
                          "(oracle/_ref/tinygemm.so, recompiled for sm_100a); single GPU only")
@@ -192,7 +281,11 @@ def main():
         if not os.path.exists(ref_so):
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/tinygemm.so not built"}))
             return
-        os.environ["ANY4_B200_OPS_LIB"] = ref_so  # any4_b200.modules / functional then drive the reference's ops
+        # benchmarking aid: register the unmodified reference extension's `tinygemm::` ops instead of this repo's and
+        # tell the package loader they are there; any4_b200.modules / functional (pure Python) then drive them
+        torch.ops.load_library(ref_so)
+        from any4_b200 import _native as _nat
+        _nat._ops_loaded = True
         args.plumbing = "torch"
     from any4_b200 import _native
     from any4_b200 import functional as tgf
@@ -201,73 +294,10 @@ def main():
     if not reference:
         tgf.set_static_weights(True)
         lib = _native.capi()
-    def note(msg):
-        if os.environ.get("LLAMA_DEBUG"):
-            print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
-
-    with torch.no_grad():
-        note("building model")
-        global _FUSED
-        _FUSED = args.exchange == "fused"
-        model = Llama(dev, rank, world, args.ctx, args.layers, args.plumbing == "fused")
-        note("model built")
-        tok = torch.tensor([1], device=dev)
-        if lib is not None:
-            lib.tg_reset_launch_count()
-        logits = model(tok)
-        torch.cuda.synchronize()
-        note("first forward done")
-        launches = int(lib.tg_launch_count()) if lib is not None else None
-        assert torch.isfinite(logits.float()).all(), "synthetic model produced non-finite logits"
-        for _ in range(args.warmup):
-            model(tok)
-        torch.cuda.synchronize()
-        note("warm-up done, capturing")
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            out = model(tok)
-        note("captured")
-        g.replay()
-        torch.cuda.synchronize()
-        note("first replay done")
-        if dist is not None:
-            dist.barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-        if dist is not None:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        clocks = sampler.stop() if sampler else None
-        del g, out  # a live CUDA graph holding NCCL kernels keeps destroy_process_group() from returning
-        torch.cuda.synchronize()
+    res = run_decode(dev, rank, world, dist, args.steps, args.warmup, args.ctx, args.layers, args.exchange, args.plumbing,
+                     args.lm_head == "any4", reference, lib)
     if rank == 0:
-        per_layer = 2 * any4_bytes(HID, HID) + 2 * any4_bytes(KV_HEADS * HEAD_DIM, HID) + 2 * any4_bytes(INTER, HID) + any4_bytes(HID, INTER)
-        quant_bytes = per_layer * args.layers
-        head_bytes = VOCAB * HID * 2
-        kv_bytes = args.layers * 2 * KV_HEADS * (args.ctx + 1) * HEAD_DIM * 2
-        total = quant_bytes / world + head_bytes + kv_bytes  # per GPU: its shard of the any4 layers, replicated head/KV
-        peak, src = measured_peak()
-        print(json.dumps({
-            "metric": "llama3_8b_any4_g128_decode_tok_per_s", "value": 1e3 / ms, "unit": "tok/s", "n_gpus": world,
-            "impl": "reference tinygemm kernels (recompiled sm_100a) in the same harness" if reference else "any4_b200",
-            "ms_per_token": ms, "steps": args.steps, "warmup": args.warmup, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "Llama-3-8B any4 g=128 single-token decode, batch 1 (BASELINE configs[2]/[4])",
-                       "layers": args.layers, "kv_context": args.ctx, "launch": "one CUDA graph per token",
-                       "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world}, exchange per Linear: {args.exchange}",
-                       "plumbing": ("q|k|v and gate|up row-fused GEMVs (silu*mul in the gate|up epilogue on 1 GPU) + any4_b200.decode kernels, 7-8 launches / layer"
-                                    if args.plumbing == "fused" else "stock torch ops, 7 GEMV launches / layer"),
-                       "lm_head": "bf16 (not quantized, as in the reference)"},
-            "bytes_per_token_per_gpu": total,
-            "roofline": {"bound": "hbm", "achieved": total / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": total / (ms * 1e-3) / 1e9 / peak, "peak_source": src + " (of measured)"},
-            "library_launches_per_token": launches, "clocks": clocks}))
+        print(json.dumps(res))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -150,6 +150,18 @@ int tg_gemm_w4_rm_sharded(void* const* y_peers, int n_peers, int64_t y_row_strid
                           int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_w4_format format, tg_dtype dtype,
                           void* stream);
 
+/* Same, with the completion of the exchange INSIDE the kernel: `flag_peers[r]` is the address of a 32-bit counter in rank
+ * r's symmetric memory (the same counter for every call that shares the output buffers; zero before the first call).
+ * When this rank's outputs are system-visible the kernel adds 1 to every rank's counter, and its last CTA returns only
+ * once this rank's own counter has reached `flag_target` - the caller passes (number of calls so far, this one
+ * included) * n_peers.  So when the kernel has completed on a rank, every rank's shard has landed in that rank's
+ * buffer: consumers are ordered by plain stream order, there is no barrier or collective launch, and programmatic
+ * dependent launch chains stay intact.  All ranks must issue the same sequence of calls. */
+int tg_gemm_w4_rm_exchange(void* const* y_peers, void* const* flag_peers, int self_rank, uint32_t flag_target, int n_peers,
+                           int64_t y_row_stride, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
+                           const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
+                           int inner_k_tiles, tg_w4_format format, tg_dtype dtype, void* stream);
+
 /* int8.  replaces tinygemm_y_f16RM_x_f16RM_w_int8TC (TinyGemm_int8.cu:215-399, :430-457).
  *   inner_k_tiles B layout: 1, 2, 4;  A layout: 1, 2 */
 int tg_gemm_w8_rm(void* y, const void* x, const int32_t* w, const void* scales_zeros, int64_t rows_x,
