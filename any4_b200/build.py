@@ -18,8 +18,9 @@ import sysconfig
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "lib")
-OBJ = os.path.join(HERE, "build")
+_VARIANT = os.environ.get("TG_BUILD_VARIANT", "")  # e.g. "_trace": a second build next to the product one (ANY4_B200_LIB_DIR)
+LIB = os.path.join(HERE, "lib" + _VARIANT)
+OBJ = os.path.join(HERE, "build" + _VARIANT)
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")

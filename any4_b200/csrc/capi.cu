@@ -30,8 +30,7 @@ int launch_gemm_w4_rm_B(void* y, const void* x, const int32_t* w, const void* sz
 int launch_gemm_w4_tc_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut, const uint8_t* exps,
                         int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik, tg_w4_format fmt, tg_dtype dt,
                         const uint16_t* const_lut, cudaStream_t st, void* const* y_peers = nullptr, int n_peers = 0,
-                        int64_t y_row_stride = 0, int silu_pairs = 0, void* const* flag_peers = nullptr, int self_rank = 0,
-                        uint32_t flag_target = 0);
+                        int64_t y_row_stride = 0, int silu_pairs = 0, int self_rank = 0, uint32_t exchange_tag = 0);
 void set_tc_ctas_per_sm(int v);
 // Automatic choice, from measurements on a B200 (profiles/r2/kernel_choice.md): the tcgen05 kernel handles 16 rows per
 // pass and wins wherever a CTA has more than a handful of ring stages to amortise its prologue; for a decode GEMV so
@@ -170,47 +169,55 @@ int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_z
                              (cudaStream_t)stream);
 }
 
-static int gemm_w4_rm_sharded_impl(const char* fn, void* const* y_peers, void* const* flag_peers, int self_rank,
-                                   uint32_t flag_target, int n_peers, int64_t y_row_stride, const void* x, const int32_t* w,
+// shared by the two row-sharded entry points; exchange_tag != 0: y_peers are the ranks' exchange buffers and y_local is
+// this rank's plain output
+static int gemm_w4_rm_sharded_impl(const char* fn, void* y_local, void* const* y_peers, int self_rank, uint32_t exchange_tag,
+                                   int n_peers, int64_t y_row_stride, const void* x, const int32_t* w,
                                    const void* scales_zeros, const void* lut, const uint8_t* exponents, int64_t rows_x,
                                    int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_w4_format format,
                                    tg_dtype dtype, void* stream) {
-  TG_REQUIRE(y_peers != nullptr && n_peers >= 1 && n_peers <= 8, "%s: 1..8 peer output pointers are required", fn);
+  TG_REQUIRE(y_peers != nullptr && n_peers >= 1 && n_peers <= 8, "%s: 1..8 peer pointers are required", fn);
   for (int r = 0; r < n_peers; ++r) TG_REQUIRE(y_peers[r] != nullptr, "%s: null peer pointer %d", fn, r);
-  if (flag_peers != nullptr) {
+  const bool exchange = exchange_tag != 0u;
+  if (exchange) {
     TG_REQUIRE(self_rank >= 0 && self_rank < n_peers, "%s: bad self_rank %d", fn, self_rank);
-    for (int r = 0; r < n_peers; ++r) TG_REQUIRE(flag_peers[r] != nullptr, "%s: null flag pointer %d", fn, r);
-  }
-  TG_REQUIRE(y_row_stride >= w_rows, "%s: output row stride (%lld) smaller than the shard (%lld)", fn,
-             (long long)y_row_stride, (long long)w_rows);
-  int rc = check_common(fn, y_peers[0], x, w, rows_x, w_rows, k, TG_WEIGHT_B, dtype);
-  if (rc != TG_OK) return rc;
-  TG_REQUIRE(format >= TG_W4_INT4 && format <= TG_W4_MX4, "%s: bad format", fn);
-  TG_REQUIRE(valid_group(group), "%s: qGroupSize must be 32, 64, 128 or 256 (got %d)", fn, group);
-  TG_REQUIRE(k % group == 0, "%s: k must be a multiple of qGroupSize", fn);
-  const int ik = inner_k_tiles;
-  TG_REQUIRE(ik == 2 || ik == 4 || ik == 8, "%s: B-layout innerKTiles must be 2, 4 or 8 (got %d)", fn, ik);
-  TG_REQUIRE((k / 16) % ik == 0, "%s: k/16 must be a multiple of innerKTiles", fn);
-  if (format == TG_W4_MX4) {
-    TG_REQUIRE(exponents != nullptr && dtype == TG_BF16, "%s: mx4 needs exponents and bf16", fn);
+    TG_REQUIRE(y_local != nullptr && (reinterpret_cast<uintptr_t>(y_local) & 3u) == 0 && y_row_stride % 2 == 0,
+               "%s: the local output must be 4-byte aligned with an even row stride", fn);
+    for (int r = 0; r < n_peers; ++r)
+      TG_REQUIRE((reinterpret_cast<uintptr_t>(y_peers[r]) & 7u) == 0, "%s: exchange buffer %d is not 8-byte aligned", fn, r);
+    TG_REQUIRE(y_row_stride >= w_rows * n_peers, "%s: output row stride (%lld) smaller than the full row (%lld)", fn,
+               (long long)y_row_stride, (long long)(w_rows * n_peers));
   } else {
-    TG_REQUIRE(scales_zeros != nullptr && aligned16(scales_zeros), "%s: scales_zeros missing or misaligned", fn);
+    y_local = y_peers[0];
+    TG_REQUIRE(y_row_stride >= w_rows, "%s: output row stride (%lld) smaller than the shard (%lld)", fn,
+               (long long)y_row_stride, (long long)w_rows);
+  }
+  int rc = check_common(fn, y_local, x, w, rows_x, w_rows, k, TG_WEIGHT_B, dtype);
+  if (rc != TG_OK) return rc;
+  TG_REQUIRE(valid_group(group), "%s: group size must be 32, 64, 128 or 256 (got %d)", fn, group);
+  TG_REQUIRE(k % group == 0, "%s: k (%lld) must be a multiple of the group size (%d)", fn, (long long)k, group);
+  TG_REQUIRE(format >= TG_W4_INT4 && format <= TG_W4_MX4, "%s: bad format", fn);
+  if (format == TG_W4_MX4) {
+    TG_REQUIRE(dtype == TG_BF16, "%s: mx4 supports bf16 activations only", fn);
+    TG_REQUIRE(exponents != nullptr, "%s: mx4 needs the exponent tensor", fn);
+  } else {
+    TG_REQUIRE(scales_zeros != nullptr, "%s: scales_and_zeros is required", fn);
+    TG_REQUIRE((reinterpret_cast<uintptr_t>(scales_zeros) & 3u) == 0, "%s: scales_and_zeros must be 4-byte aligned", fn);
   }
   if (format == TG_W4_ANY4_GLOBAL || format == TG_W4_ANY4_ROWWISE)
-    TG_REQUIRE(lut != nullptr && aligned16(lut), "%s: any4 LUT missing or misaligned", fn);
+    TG_REQUIRE(lut != nullptr && aligned16(lut), "%s: any4 needs a 16-byte aligned LUT", fn);
+  const int ik = inner_k_tiles == 0 ? 4 : inner_k_tiles;
   if (rows_x == 0) return TG_OK;
   const uint16_t* clut = nullptr;
   if (format == TG_W4_INT4 || format == TG_W4_MX4) {
     rc = const_lut_for(format, dtype, (cudaStream_t)stream, &clut);
     if (rc != TG_OK) return rc;
   }
-  // the peer-store epilogue lives in the tcgen05 kernel (the in-kernel completion needs it; the mma.sync kernel keeps
-  // a plain peer-store variant for TG_OPT_W4_KERNEL = 2)
-  if (flag_peers != nullptr || !use_mma_sync_b(rows_x, w_rows, k))
-    return launch_gemm_w4_tc_B(y_peers[0], x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
-                               clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride, 0, flag_peers, self_rank,
-                               flag_target);
-  return launch_gemm_w4_rm_B(y_peers[0], x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
+  // the in-kernel exchange lives in the tcgen05 kernel; the mma.sync kernel keeps a plain peer-store variant
+  if (exchange || !use_mma_sync_b(rows_x, w_rows, k))
+    return launch_gemm_w4_tc_B(y_local, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
+                               clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride, 0, self_rank, exchange_tag);
+  return launch_gemm_w4_rm_B(y_local, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
                              clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride);
 }
 
@@ -218,18 +225,18 @@ int tg_gemm_w4_rm_sharded(void* const* y_peers, int n_peers, int64_t y_row_strid
                           const void* scales_zeros, const void* lut, const uint8_t* exponents, int64_t rows_x,
                           int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_w4_format format, tg_dtype dtype,
                           void* stream) {
-  return gemm_w4_rm_sharded_impl("tg_gemm_w4_rm_sharded", y_peers, nullptr, 0, 0, n_peers, y_row_stride, x, w, scales_zeros,
-                                 lut, exponents, rows_x, w_rows, k, group, inner_k_tiles, format, dtype, stream);
+  return gemm_w4_rm_sharded_impl("tg_gemm_w4_rm_sharded", nullptr, y_peers, 0, 0u, n_peers, y_row_stride, x, w,
+                                 scales_zeros, lut, exponents, rows_x, w_rows, k, group, inner_k_tiles, format, dtype, stream);
 }
 
-int tg_gemm_w4_rm_exchange(void* const* y_peers, void* const* flag_peers, int self_rank, uint32_t flag_target, int n_peers,
-                           int64_t y_row_stride, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
+int tg_gemm_w4_rm_exchange(void* y, void* const* xchg_peers, int self_rank, uint32_t tag, int n_peers, int64_t y_row_stride,
+                           const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
                            const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
                            int inner_k_tiles, tg_w4_format format, tg_dtype dtype, void* stream) {
   const char* fn = "tg_gemm_w4_rm_exchange";
-  TG_REQUIRE(flag_peers != nullptr, "%s: flag pointers are required", fn);
-  return gemm_w4_rm_sharded_impl(fn, y_peers, flag_peers, self_rank, flag_target, n_peers, y_row_stride, x, w, scales_zeros,
-                                 lut, exponents, rows_x, w_rows, k, group, inner_k_tiles, format, dtype, stream);
+  TG_REQUIRE(tag != 0u, "%s: the call tag must not be 0", fn);
+  return gemm_w4_rm_sharded_impl(fn, y, xchg_peers, self_rank, tag, n_peers, y_row_stride, x, w, scales_zeros, lut,
+                                 exponents, rows_x, w_rows, k, group, inner_k_tiles, format, dtype, stream);
 }
 
 int tg_gemm_w4_rm_silu_pairs(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,

@@ -63,10 +63,20 @@ constexpr int kCtrlHl = 240;                // odd half-lines 240.. hold the mba
 constexpr int kXResMaxStages = 14;          // resident activations: 16 half-lines per 1024 k -> k <= 14336
 constexpr int kMaxGrid = 512;
 constexpr int kWsPools = 4;
+// Two scheduling experiments, measured on a B200 and left OFF (profiles/r2/EXPERIMENTS.md): neither moves the m = 1
+// kernel (the SM is instruction-issue bound: a stall of one CTA is absorbed by the co-resident one) and the deferred
+// epilogue costs the single-accumulator m = 16 kernel 20 %.
+#ifndef TG_TC_EARLY_RELEASE
+#define TG_TC_EARLY_RELEASE 0
+#endif
+#ifndef TG_TC_DEFER
+#define TG_TC_DEFER 0
+#endif
+constexpr bool kEarlyRelease = TG_TC_EARLY_RELEASE != 0;  // hand a ring stage back as soon as its bytes are in registers
+constexpr bool kDefer = TG_TC_DEFER != 0;                  // read a row block's sums one stage into the next row block
 
 // split fix-up workspace: tagged fp32 partial sums [pool][CTA][slot 0/1][mi][row], one 8-byte word (value, launch tag) each
 __device__ unsigned long long g_ws_partial[kWsPools][kMaxGrid * 2 * 16 * 32];
-__device__ unsigned g_ws_done[kWsPools];  // CTAs of a launch that have finished (row-sharded exchange, self-resetting)
 
 struct ParamsTC {
   const uint8_t* w;      // packed weight
@@ -77,7 +87,6 @@ struct ParamsTC {
   const uint16_t* lut;   // [16] or [w_rows][16]
   unsigned long long* ws_partial;  // this launch's workspace pool
   uint32_t ws_tag;                  // launch tag carried by every partial of this launch
-  unsigned* ws_done;                // finished-CTA counter of this launch (row-sharded exchange only)
   int64_t tile_stride;   // bytes between consecutive n-tiles of the packed weight = 4 * k
   int64_t y_stride;
   int lut_stride;        // 0 or 16
@@ -366,9 +375,19 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
   };
 
   if (warp == kDqWarps) {
+    // the weight stream starts first thing: the ring has kWStages free stages, nobody has to be asked, and only the
+    // three "full" barriers have to exist; the other barriers are set up while the first bytes are on their way
+    if (lane == 0) {
+      for (int i = 0; i < 3; ++i) mbar_init(sbase + bar_off(B_WFULL + i), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      TC_TRACE(16);
+    }
+    __syncwarp();
+    pol = l2_evict_first_policy();
+    for (int i = 0; i < kWStages && pc.u < u_end; ++i) produce();
     if (lane == 0) {
       for (int i = 0; i < 3; ++i) {
-        mbar_init(sbase + bar_off(B_WFULL + i), 1);
         mbar_init(sbase + bar_off(B_WEMPTY + i), kDqWarps);
         mbar_init(sbase + bar_off(B_AFULL + i), 4);
         mbar_init(sbase + bar_off(B_AEMPTY + i), 1);
@@ -379,12 +398,8 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      TC_TRACE(16);
     }
     __syncwarp();
-    // the weight stream starts right here: the ring has kWStages free stages, nobody has to be asked
-    pol = l2_evict_first_policy();
-    for (int i = 0; i < kWStages && pc.u < u_end; ++i) produce();
   } else if (warp == kDqWarps + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kHolderOff), "r"(256u)
                  : "memory");
@@ -547,11 +562,120 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
     Cursor cur;
     cur.init(u_begin, S);
     const int rb_first = cur.rb;
+
+    // ---- epilogue of one row-block segment: accumulators -> row sums -> y (or the split fix-up workspace) ----
+    // Software pipelined: the dequant warps do NOT drain at a row-block boundary.  They build the next pair table and
+    // dequantise the next block's first stage while the tensor core finishes the previous block (the accumulators are
+    // double buffered; with one buffer, MB = 16, the issuer simply holds the next block's MMAs until `finish` has
+    // released it - by then at most 2 of the 3 A slots are waiting), and only then read the sums, which are long
+    // complete.  Only the last segment of a CTA waits for its MMAs.
+    bool pend_on = false, pend_mid = false;
+    int pend_rb = 0, pend_first = 0, pend_n = 0;
+    auto finish = [&](int rb, int seg_first, int seg_n, bool last) {
+      const int row0 = rb * 32;
+      // accumulators -> red[j][mi][lane] (quad 0's warps cover the four TMEM sub-partitions)
+      if (Q == 0) {
+        const int buf = (int)(dseq % C::NB);
+        mbar_wait(sbase + bar_off(B_DFULL + buf), (dseq / C::NB) & 1u);
+        tc_fence_after();
+        if (threadIdx.x == 0 && last) TC_TRACE(12);
+        const uint32_t dcol = my_tmem + (uint32_t)(buf * C::N + j);
+        uint32_t v[MB];
+#pragma unroll
+        for (int mi = 0; mi < MB; ++mi)
+          if (mi < p.m) v[mi] = tmem_ld1(dcol + (uint32_t)(mi * 4));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int mi = 0; mi < MB; ++mi)
+          if (mi < p.m) sts32(sbase + odd_hl(C::kRedHl0 + j * MB + mi) + lane4, v[mi]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sbase + bar_off(B_DEMPTY + buf));
+      }
+      ++dseq;
+      bar_sync(1, kDqThreads);
+
+      // row sums: thread idx -> (mi, row); the four quarters' partials added in order
+      const bool complete = (seg_first == 0 && seg_n == S);
+      const int rows_valid = min(32, p.w_rows - row0);
+      auto emit = [&](int mi, int rr, float total) {
+        if constexpr (PEERS) {
+          if (peers.tag != 0u) {  // in-kernel exchange: rows (rr, rr + 1) travel as one tagged 8-byte word to every rank
+            const uint32_t mine = f32_to_dt<DT>(total);
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+            if (!(rr & 1) && rr < rows_valid) {
+              const unsigned long long word = ((unsigned long long)peers.tag << 32) | (unsigned long long)(mine | (other << 16));
+              const int64_t widx = (int64_t)mi * (peers.n_total >> 1) + ((peers.col0 + row0 + rr) >> 1);
+#pragma unroll 1
+              for (int r = 0; r < peers.n; ++r)
+                asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(peers.y[r]) + widx), "l"(word)
+                             : "memory");
+            }
+            return;
+          }
+        }
+        if (p.flags & 16) {  // (gate, up) row pairs -> silu(gate) * up
+          const uint32_t mine = f32_to_dt<DT>(total);
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+          if (!(rr & 1) && rr < rows_valid)
+            store_out<PEERS>(p.y, peers, (int64_t)mi * p.y_stride + ((row0 + rr) >> 1), silu_mul_dt<DT>((uint16_t)mine, (uint16_t)other));
+        } else if (rr < rows_valid) {
+          store_out<PEERS>(p.y, peers, (int64_t)mi * p.y_stride + row0 + rr, f32_to_dt<DT>(total));
+        }
+      };
+      auto block_sum = [&](int mi, int rr) {
+        const uint32_t a = sbase + odd_hl(C::kRedHl0 + mi) + (uint32_t)row_of_lane(rr) * 4u;
+        float total = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) total += __uint_as_float(lds32(a + (uint32_t)(q * MB) * 256u));
+        return total;
+      };
+      if (complete) {
+        for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) emit(idx >> 5, idx & 31, block_sum(idx >> 5, idx & 31));
+      } else {
+        // Row block shared with other CTAs.  The CTA that holds the block's FIRST stages owns the result: that segment
+        // is the last thing the CTA does, while the other CTAs meet the block at the very beginning of their ranges,
+        // so their partials are long there.  A partial travels as ONE 8-byte word (value, launch tag): whoever sees
+        // the tag sees the value, so no fence, no atomic and no counter is needed (a fence would wait ~2 us for this
+        // thread's prefetched group words to come back behind the weight stream).  The owner adds the partials in CTA
+        // order: deterministic.
+        const int me = (int)blockIdx.x;
+        const int i_first = cta_of_unit(p, rb * S);
+        const int i_last = cta_of_unit(p, rb * S + S - 1);
+        for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) {
+          float total = block_sum(idx >> 5, idx & 31);
+          if (me != i_first) {
+            const int slot = rb == rb_first ? 0 : 1;
+            const unsigned long long word = ((unsigned long long)p.ws_tag << 32) | (unsigned long long)__float_as_uint(total);
+            asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p.ws_partial + ((size_t)(me * 2 + slot) * 16) * 32 + idx), "l"(word)
+                         : "memory");
+          } else {
+            for (int ii = i_first + 1; ii <= i_last; ++ii) {
+              int b0, e0;
+              cta_range(p, ii, b0, e0);
+              const int sl = (b0 / S == rb) ? 0 : 1;
+              unsigned long long* src = p.ws_partial + ((size_t)(ii * 2 + sl) * 16) * 32 + idx;
+              unsigned long long word;
+              do {
+                asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(word) : "l"(src) : "memory");
+              } while ((uint32_t)(word >> 32) != p.ws_tag);
+              // consumed: clear the word.  A CUDA-graph replay re-launches this kernel with the SAME tag; without the
+              // clear its owner could take this launch's partial for its own.  (The next writer of this word is a
+              // launch that starts its stores only after this one has completed.)
+              asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(src), "l"(0ull) : "memory");
+              total += __uint_as_float((uint32_t)word);
+            }
+            emit(idx >> 5, idx & 31, total);
+          }
+        }
+      }
+      if (threadIdx.x == 0 && last) TC_TRACE(13);
+    };
+
     while (cur.u < u_end) {
       const int rb = cur.rb;
       const int seg_first = cur.sir;
       const int seg_n = min(S - cur.sir, u_end - cur.u);  // stages of this row block done by this CTA
-      const int row0 = rb * 32;
 
       // ---- pair table of this row block (its LUT rows were requested one row block ago) ----
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -643,6 +767,13 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
               W[u][0] = v.x, W[u][1] = v.y, W[u][2] = v.z, W[u][3] = v.w;
             }
           }
+          // The stage's bytes now live in registers: hand the ring slot back to the producer right away (the arrive is
+          // a release: it orders the loads above, of all lanes after the __syncwarp, before the refill), so the next
+          // bulk copy into this slot is in flight during the whole dequant of the stage.
+          if constexpr (kEarlyRelease) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sbase + bar_off(B_WEMPTY) + ws * 8u);
+          }
           // probe the next stage's weights now: the answer arrives while this stage's lookups issue
           w_ready = more ? mbar_test(sbase + bar_off(B_WFULL) + ws_n * 8u, wpar_n) : 0u;
           uint32_t r0[8];
@@ -689,7 +820,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(sbase + bar_off(B_AFULL) + as * 8u);
-          mbar_arrive(sbase + bar_off(B_WEMPTY) + ws * 8u);  // hand the weight stage back to the producer
+          if (!kEarlyRelease || kt_valid < 8) mbar_arrive(sbase + bar_off(B_WEMPTY) + ws * 8u);  // (k tail: word loads all along the stage)
         }
         if (free_uses > 0) --free_uses;
         // probe this quad's next A slot (previous use: the OTHER quad's stage before ours); consumed one stage later
@@ -697,108 +828,46 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
         if (threadIdx.x == 0 && gst < 4) TC_TRACE(22 + gst * 4);
         ws = ws_n, wpar = wpar_n;
         as = as_n, apar = apar_n;
+        pend_mid = false;
+        if (kDefer && pend_on) {  // (i == 0) the previous row block's sums: complete by now, nobody waits
+          finish(pend_rb, pend_first, pend_n, false);
+          pend_on = false, pend_mid = true;
+        }
       }
       cur.skip(seg_n, S);
       if (threadIdx.x == 0 && first_seg) TC_TRACE(11);
-
-      // ---- accumulators -> red[j][mi][lane] (quad 0's warps cover the four TMEM sub-partitions) ----
-      if (Q == 0) {
-        const int buf = (int)(dseq % C::NB);
-        mbar_wait(sbase + bar_off(B_DFULL + buf), (dseq / C::NB) & 1u);
-        tc_fence_after();
-        if (threadIdx.x == 0 && first_seg) TC_TRACE(12);
-        const uint32_t dcol = my_tmem + (uint32_t)(buf * C::N + j);
-        uint32_t v[MB];
-#pragma unroll
-        for (int mi = 0; mi < MB; ++mi)
-          if (mi < p.m) v[mi] = tmem_ld1(dcol + (uint32_t)(mi * 4));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int mi = 0; mi < MB; ++mi)
-          if (mi < p.m) sts32(sbase + odd_hl(C::kRedHl0 + j * MB + mi) + lane4, v[mi]);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sbase + bar_off(B_DEMPTY + buf));
-      }
-      ++dseq;
-      bar_sync(1, kDqThreads);
-
-      // ---- row sums: thread idx -> (mi, row); the four quarters' partials added in order ----
-      const bool complete = (seg_first == 0 && seg_n == S);
-      const int rows_valid = min(32, p.w_rows - row0);
-      auto emit = [&](int mi, int rr, float total) {
-        if (p.flags & 16) {  // (gate, up) row pairs -> silu(gate) * up
-          const uint32_t mine = f32_to_dt<DT>(total);
-          const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
-          if (!(rr & 1) && rr < rows_valid)
-            store_out<PEERS>(p.y, peers, (int64_t)mi * p.y_stride + ((row0 + rr) >> 1), silu_mul_dt<DT>((uint16_t)mine, (uint16_t)other));
-        } else if (rr < rows_valid) {
-          store_out<PEERS>(p.y, peers, (int64_t)mi * p.y_stride + row0 + rr, f32_to_dt<DT>(total));
-        }
-      };
-      auto block_sum = [&](int mi, int rr) {
-        const uint32_t a = sbase + odd_hl(C::kRedHl0 + mi) + (uint32_t)row_of_lane(rr) * 4u;
-        float total = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) total += __uint_as_float(lds32(a + (uint32_t)(q * MB) * 256u));
-        return total;
-      };
-      if (complete) {
-        for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) emit(idx >> 5, idx & 31, block_sum(idx >> 5, idx & 31));
-      } else {
-        // Row block shared with other CTAs.  The CTA that holds the block's FIRST stages owns the result: that segment
-        // is the last thing the CTA does, while the other CTAs meet the block at the very beginning of their ranges,
-        // so their partials are long there.  A partial travels as ONE 8-byte word (value, launch tag): whoever sees
-        // the tag sees the value, so no fence, no atomic and no counter is needed (a fence would wait ~2 us for this
-        // thread's prefetched group words to come back behind the weight stream).  The owner adds the partials in CTA
-        // order: deterministic.
-        const int me = (int)blockIdx.x;
-        const int i_first = cta_of_unit(p, rb * S);
-        const int i_last = cta_of_unit(p, rb * S + S - 1);
-        for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) {
-          float total = block_sum(idx >> 5, idx & 31);
-          if (me != i_first) {
-            const int slot = rb == rb_first ? 0 : 1;
-            const unsigned long long word = ((unsigned long long)p.ws_tag << 32) | (unsigned long long)__float_as_uint(total);
-            asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p.ws_partial + ((size_t)(me * 2 + slot) * 16) * 32 + idx), "l"(word)
-                         : "memory");
-          } else {
-            for (int ii = i_first + 1; ii <= i_last; ++ii) {
-              int b0, e0;
-              cta_range(p, ii, b0, e0);
-              const int sl = (b0 / S == rb) ? 0 : 1;
-              const unsigned long long* src = p.ws_partial + ((size_t)(ii * 2 + sl) * 16) * 32 + idx;
-              unsigned long long word;
-              do {
-                asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(word) : "l"(src) : "memory");
-              } while ((uint32_t)(word >> 32) != p.ws_tag);
-              total += __uint_as_float((uint32_t)word);
-            }
-            emit(idx >> 5, idx & 31, total);
-          }
-        }
-      }
-      if (threadIdx.x == 0 && first_seg) TC_TRACE(13);
+      // this row block's sums are read one stage into the NEXT row block (or after the loop): see `finish`
+      pend_on = true, pend_rb = rb, pend_first = seg_first, pend_n = seg_n;
       first_seg = false;
+      if (!kDefer) {
+        finish(pend_rb, pend_first, pend_n, cur.u >= u_end);
+        pend_on = false;
+      }
+    }
+    if (pend_on) {
+      if (pend_mid) bar_sync(1, kDqThreads);  // the deferred epilogue of this very stage may still be reading `red`
+      finish(pend_rb, pend_first, pend_n, true);
     }
     if (threadIdx.x == 0) TC_TRACE(14);
     if constexpr (PEERS) {
-      if (peers.my_flag != nullptr) {
-        // in-kernel completion of the exchange (see w4::Peers)
-        bar_sync(1, kDqThreads);  // every peer store of this CTA has been issued
-        if (threadIdx.x == 0) {
-          __threadfence_system();  // ... and is visible system-wide
-          const unsigned done = atomicAdd(p.ws_done, 1u);
-          if (done == gridDim.x - 1u) {  // the launch's last CTA signals for the whole rank
-            *p.ws_done = 0u;
-            __threadfence_system();
-            for (int r = 0; r < peers.n; ++r)
-              asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(peers.flag[r]) : "memory");
-            uint32_t v;
-            do {
-              asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(peers.my_flag) : "memory");
-            } while ((int32_t)(v - peers.target) < 0);
-          }
+      if (peers.tag != 0u) {
+        // collect this CTA's slice of the full output from the local exchange buffer (all ranks store into it, ours
+        // included): spin until a word carries this call's tag, then write its two values to the plain output
+        const int half = peers.n_total >> 1;
+        const int words = p.m * half;
+        const int lo = (int)(((int64_t)words * (int)blockIdx.x) / (int)gridDim.x);
+        const int hi = (int)(((int64_t)words * ((int)blockIdx.x + 1)) / (int)gridDim.x);
+        unsigned long long* ll = reinterpret_cast<unsigned long long*>(peers.y[peers.self]);
+        for (int wi = lo + (int)threadIdx.x; wi < hi; wi += kDqThreads) {
+          unsigned long long word;
+          do {
+            asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(word) : "l"(ll + wi) : "memory");
+          } while ((uint32_t)(word >> 32) != peers.tag);
+          // consumed: clear the word, so that the buffer's next use (>= 2 calls later, possibly a CUDA-graph replay
+          // of this very launch with the same tag) starts from words without a tag
+          asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(ll + wi), "l"(0ull) : "memory");
+          const int mi = wi / half, c = wi - mi * half;
+          *reinterpret_cast<uint32_t*>(p.y + (int64_t)mi * p.y_stride + 2 * c) = (uint32_t)word;
         }
       }
     }
@@ -956,7 +1025,6 @@ int g_split = -1;       // -1 = heuristic, 0 = whole row blocks per CTA, 1 = str
 struct DeviceInfo {
   int n_sm = 0;
   unsigned long long* ws_partial = nullptr;
-  unsigned* ws_done = nullptr;
 };
 static int device_info(DeviceInfo** out) {
   static thread_local DeviceInfo info[kMaxDevices];
@@ -966,8 +1034,7 @@ static int device_info(DeviceInfo** out) {
     cudaGetDevice(&dev);
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    if (cudaGetSymbolAddress((void**)&d.ws_partial, g_ws_partial) != cudaSuccess ||
-        cudaGetSymbolAddress((void**)&d.ws_done, g_ws_done) != cudaSuccess) {
+    if (cudaGetSymbolAddress((void**)&d.ws_partial, g_ws_partial) != cudaSuccess) {
       set_error("cudaGetSymbolAddress failed: %s", cudaGetErrorString(cudaGetLastError()));
       return TG_ERR_CUDA;
     }
@@ -1039,7 +1106,6 @@ int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) 
   const unsigned seq = g_launch_seq.fetch_add(1u, std::memory_order_relaxed) + 1u;  // process-wide: tags must be unique
   p.ws_partial = di->ws_partial + (size_t)(seq % kWsPools) * (kMaxGrid * 2 * 16 * 32);
   p.ws_tag = seq;
-  p.ws_done = di->ws_done + (seq % kWsPools);
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)G, 1, 1);
@@ -1083,7 +1149,8 @@ int launch_m(ParamsTC p, const Peers& peers0, int row_blocks, int64_t rows_x, co
     p.m = (int)((rows_x - r0) < per_pass ? (rows_x - r0) : per_pass);
     p.x = x + r0 * p.k;
     p.y = y + r0 * p.y_stride;
-    for (int r = 0; r < peers0.n; ++r) peers.y[r] = peers0.y[r] + r0 * p.y_stride;
+    for (int r = 0; r < peers0.n; ++r)  // plain peer stores: element offset; exchange: 8-byte words [m][n_total / 2]
+      peers.y[r] = peers0.y[r] + (peers0.tag != 0u ? r0 * (peers0.n_total >> 1) * 4 : r0 * p.y_stride);
     int rc;
     const bool res = p.m == 1 && p.stages_per_row <= kXResMaxStages;
     // the decode kernel (one activation row) is specialised for groups >= 128 (one group word per stage)
@@ -1117,16 +1184,15 @@ int launch_ik(const ParamsTC& p, const Peers& peers, int ik, int row_blocks, int
 int launch_gemm_w4_tc_B(void* y, const void* x, const int32_t* w, const void* sz, const void* lut, const uint8_t* exps,
                         int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik, tg_w4_format fmt, tg_dtype dt,
                         const uint16_t* const_lut, cudaStream_t st, void* const* y_peers, int n_peers, int64_t y_row_stride,
-                        int silu_pairs, void* const* flag_peers, int self_rank, uint32_t flag_target) {
+                        int silu_pairs, int self_rank, uint32_t exchange_tag) {
   tc::ParamsTC p{};
   w4::Peers peers{};
   peers.n = n_peers;
   for (int r = 0; r < n_peers; ++r) peers.y[r] = static_cast<uint16_t*>(y_peers[r]);
-  if (flag_peers != nullptr) {
-    for (int r = 0; r < n_peers; ++r) peers.flag[r] = static_cast<uint32_t*>(flag_peers[r]);
-    peers.my_flag = peers.flag[self_rank];
-    peers.target = flag_target;
-  }
+  peers.tag = exchange_tag;  // != 0: y_peers are the ranks' exchange buffers, y is the plain local output
+  peers.self = self_rank;
+  peers.n_total = (int)(w_rows * n_peers);
+  peers.col0 = (int)(w_rows * self_rank);
   p.w = reinterpret_cast<const uint8_t*>(w);
   p.sz = (fmt == TG_W4_MX4) ? nullptr : reinterpret_cast<const uint32_t*>(sz);
   p.exps = (fmt == TG_W4_MX4) ? exps : nullptr;

@@ -154,13 +154,17 @@ __device__ __forceinline__ void l2_prefetch_line(const void* src) {
 // outputs to all of them over NVLink (peer pointers are ordinary UVA addresses).
 struct Peers {
   uint16_t* y[8];
-  // optional in-kernel completion of the exchange (tg_gemm_w4_rm_exchange): flag[r] = rank r's copy of a counter in
-  // symmetric memory.  The last CTA of the launch adds 1 to every rank's counter once all of this rank's stores are
-  // system-visible, then waits until its own copy reaches `target` (= every rank has done the same): when the kernel
-  // completes, all ranks' shards have landed in this rank's buffer - no barrier kernel, the PDL chain stays intact.
-  uint32_t* flag[8];
-  uint32_t* my_flag;
-  uint32_t target;
+  // In-kernel exchange (tg_gemm_w4_rm_exchange), tag != 0: y[r] is NOT an output buffer but rank r's copy of a
+  // symmetric exchange buffer of 8-byte words [m][n_total / 2], word = (tag << 32) | two adjacent bf16/fp16 outputs.
+  // The epilogue stores this rank's shard as tagged words into every rank's copy (one 8-byte store per word and peer:
+  // whoever sees the tag sees the values, so no fence, no flag and no barrier is needed - the NCCL "LL" idea), and
+  // before a CTA exits it collects its slice of ALL ranks' words from the local copy (spinning on the tag) into the
+  // plain local output p.y.  When the kernel has completed on a rank, the full m x n_total output is in that rank's
+  // p.y: consumers are ordered by plain stream order / programmatic dependent launch.
+  uint32_t tag;
+  int self;      // this rank
+  int n_total;   // full output width = n * shard rows
+  int col0;      // first output column of this rank's shard
   int n;
 };
 template <bool PEERS>

@@ -224,11 +224,11 @@ def _fuse_rows_interleaved(linears):
 
 
 class _SymmWorkspace:
-    """One peer-mapped (symmetric-memory) output workspace per (process group, device): a ring of `SLOTS` m x n buffers
-    every rank can store into directly, plus the exchange counter of tg_gemm_w4_rm_exchange.  Shared by all
-    RowShardedLinear layers of the process.
+    """Per (process group, device): the symmetric-memory exchange buffers of tg_gemm_w4_rm_exchange (a ring of `SLOTS`
+    buffers of 8-byte tagged words, peer-mapped so every rank can store into every other rank's copy) and a ring of
+    `SLOTS` plain local m x n output buffers.  Shared by all RowShardedLinear layers of the process.
 
-    Contract: the tensor a fused sharded forward returns is a VIEW of ring slot `call % SLOTS`; it stays valid until
+    Contract: the tensor a fused sharded forward returns is a VIEW of output slot `call % SLOTS`; it stays valid until
     SLOTS - 1 further fused sharded calls (of any layer) have been issued on this rank.  Consume it (or copy it) before
     that.  Every rank must issue the same sequence of fused sharded calls."""
 
@@ -240,16 +240,15 @@ class _SymmWorkspace:
         import torch.distributed._symmetric_memory as symm
 
         group = group if group is not None else dist.group.WORLD
+        n_cap += n_cap & 1
         self.m_cap, self.n_cap = m_cap, n_cap
-        self.buf = symm.empty((self.SLOTS, m_cap, n_cap), dtype=dtype, device=device)
-        self.hdl = symm.rendezvous(self.buf, group)
+        self.xchg = symm.empty((self.SLOTS, m_cap, n_cap // 2), dtype=torch.int64, device=device)
+        self.xchg.zero_()  # tag 0 is never used by a call
+        self.hdl = symm.rendezvous(self.xchg, group)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        self.flags = symm.empty((16,), dtype=torch.int32, device=device)
-        self.flags.zero_()
-        self.flag_hdl = symm.rendezvous(self.flags, group)
-        self.flag_ptrs = [int(p) for p in self.flag_hdl.buffer_ptrs]
+        self.out = torch.empty((self.SLOTS, m_cap, n_cap), dtype=dtype, device=device)
         torch.cuda.synchronize(device)
-        dist.barrier(group)  # every rank's counter is zero before anybody adds to it
+        dist.barrier(group)  # every rank's exchange buffer is zero before anybody stores into it
         self.calls = 0
 
     @classmethod
@@ -348,18 +347,18 @@ class RowShardedLinear(torch.nn.Module):
         ws = _SymmWorkspace.get(self.group, x2d.device, x2d.dtype, m, self.max_features)
         slot = ws.calls % ws.SLOTS
         ws.calls += 1
-        elt = x2d.element_size()
-        base = (slot * ws.m_cap * ws.n_cap + self.lo) * elt   # this shard's first column in ring slot `slot`
-        peers = (ctypes.c_void_p * self.world)(*[p + base for p in ws.ptrs])
-        flags = (ctypes.c_void_p * self.world)(*ws.flag_ptrs)
+        tag = ((ws.calls - 1) % 0xFFFFFFFF) + 1            # non-zero, unique per call
+        out = ws.out[slot]
+        xoff = slot * ws.m_cap * (ws.n_cap // 2) * 8       # this call's exchange buffer: the start of ring slot `slot`
+        peers = (ctypes.c_void_p * self.world)(*[p + xoff for p in ws.ptrs])
         is_any4 = hasattr(loc, "lut")
         fmt = (2 if loc.lut.dim() == 2 else 1) if is_any4 else 0  # tg_w4_format
         lib = _native.capi()
         with torch.cuda.device(x2d.device):
-            # the exchange completes INSIDE the kernel (its last CTA waits until every rank's shard has landed here):
-            # no barrier / collective launch follows, consumers are ordered by plain stream order
+            # the exchange completes INSIDE the kernel (tagged words into every rank's buffer, every CTA collects its
+            # slice before it exits): no barrier / collective launch follows, consumers are ordered by stream order
             rc = lib.tg_gemm_w4_rm_exchange(
-                peers, flags, self.rank, (ws.calls * self.world) & 0xFFFFFFFF, self.world, ws.n_cap,
+                ctypes.c_void_p(out.data_ptr()), peers, self.rank, tag, self.world, ws.n_cap,
                 ctypes.c_void_p(x2d.data_ptr()), ctypes.c_void_p(loc.weight.data_ptr()),
                 ctypes.c_void_p(loc.scales_and_zeros.data_ptr()),
                 ctypes.c_void_p(loc.lut.data_ptr()) if is_any4 else None, None,
@@ -367,4 +366,4 @@ class RowShardedLinear(torch.nn.Module):
                 0 if x2d.dtype == torch.bfloat16 else 1, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc != 0:
             raise RuntimeError(_native.last_error())
-        return ws.buf[slot, :m, :n]
+        return out[:m, :n]

@@ -247,6 +247,8 @@ def run_ours(args):
 
     tgf.set_static_weights(True)  # every layer below is packed once, before the timed region
 
+    parity = {"checked": world > 1, "ok": True}
+
     def build_layers(n, k, copies):
         layers = []
         for i in range(copies):
@@ -254,8 +256,23 @@ def run_ours(args):
             w, lut, sz = synth_layer(n, k, 1234 + i, dev)
             lin.weight.data, lin.lut.data, lin.scales_and_zeros.data = w, lut, sz
             lin.weight_reshaped = True
-            layers.append(RowShardedLinear(lin, rank, world, fused=args.exchange == "fused", max_features=11008)
-                          if world > 1 else lin)
+            if world > 1:
+                sh = RowShardedLinear(lin, rank, world, fused=args.exchange == "fused", max_features=11008)
+                if i == 0:
+                    # driver-visible parity of the N > 1 path, before anything is timed: the sharded output (every
+                    # rank's copy) against the single-GPU output of the same layer, m = 1 and m = 5.  Same dequantised
+                    # weights and exact products; a shard of n / N rows may get another k-split than the full layer, so
+                    # the fp32 summation ORDER (the last bf16 bit of a few outputs) may differ - nothing else may.
+                    for m in (1, 5):
+                        xp = torch.randn(m, k, device=dev, generator=torch.Generator(device=dev).manual_seed(5 + m)).bfloat16()
+                        got, want = sh(xp).float(), lin(xp).float()   # (every rank makes the same calls, whatever `ok` is)
+                        close = bool(((got - want).abs() <= 2.0 ** -7 * want.abs() + 2.0 ** -9 * want.abs().max()).all())
+                        same = float((got == want).float().mean())
+                        parity["ok"] = parity["ok"] and close and same > 0.98
+                        parity["frac_bit_equal"] = min(parity.get("frac_bit_equal", 1.0), same)
+                layers.append(sh)
+            else:
+                layers.append(lin)
         return layers
 
     def bench_shape(n, k, steps, warmup, with_e2e):
@@ -368,6 +385,12 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline()
 
+    if dist is not None:
+        t = torch.tensor([1 if parity["ok"] else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        parity["ok"] = bool(t.item())
+        if not parity["ok"]:
+            raise SystemExit("bench.py: the row-sharded output differs from the single-GPU output - nothing timed is valid")
     if rank == 0:
         nbytes = algorithmic_bytes(HEADLINE, HEADLINE)
         per_rank_bytes = nbytes / world  # each rank streams 1/world of the rows (x replicated, negligible)
@@ -384,7 +407,7 @@ def run_ours(args):
                 "l2_policy": f"inputs larger than L2: {head['copies']} distinct weight sets = "
                              f"{head['copies'] * nbytes / 1e6:.0f} MB rotated every step",
                 "parallelism": "1 GPU" if world == 1 else (
-                    f"row-sharded x{world}, exchange fused into the GEMV epilogue (peer stores over NVLink + barrier)"
+                    f"row-sharded x{world}, exchange fused into the GEMV epilogue (peer stores over NVLink, completion counter in symmetric memory, no barrier / collective launch)"
                     if args.exchange == "fused" else f"row-sharded x{world} + NCCL all-reduce on y"),
                 "other_shapes": {f"{e['n']}x{e['k']}": {"GBps": round(e["gbps"], 1), "us_per_gemv": round(e["us_per_gemv"], 3),
                                                          "frac_of_peak": round(e["gbps"] / world / peak, 4)} for e in extra},
@@ -396,6 +419,8 @@ def run_ours(args):
             "e2e": {"value": head["e2e_gbps"], "unit": "GB/s", "h2d_bytes_per_step": head["h2d"],
                     "d2h_bytes_per_step": head["d2h"]},
             "gpu_launches": head["launches"],
+            "parity_checked": (parity["ok"] if parity["checked"] else None),
+            "parity_frac_bit_equal": parity.get("frac_bit_equal"),
             "clocks": clocks,
         }
         if cpu is not None:

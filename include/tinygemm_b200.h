@@ -150,15 +150,21 @@ int tg_gemm_w4_rm_sharded(void* const* y_peers, int n_peers, int64_t y_row_strid
                           int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_w4_format format, tg_dtype dtype,
                           void* stream);
 
-/* Same, with the completion of the exchange INSIDE the kernel: `flag_peers[r]` is the address of a 32-bit counter in rank
- * r's symmetric memory (the same counter for every call that shares the output buffers; zero before the first call).
- * When this rank's outputs are system-visible the kernel adds 1 to every rank's counter, and its last CTA returns only
- * once this rank's own counter has reached `flag_target` - the caller passes (number of calls so far, this one
- * included) * n_peers.  So when the kernel has completed on a rank, every rank's shard has landed in that rank's
- * buffer: consumers are ordered by plain stream order, there is no barrier or collective launch, and programmatic
- * dependent launch chains stay intact.  All ranks must issue the same sequence of calls. */
-int tg_gemm_w4_rm_exchange(void* const* y_peers, void* const* flag_peers, int self_rank, uint32_t flag_target, int n_peers,
-                           int64_t y_row_stride, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
+/* Row-sharded GEMV with the exchange INSIDE the kernel (no collective, no barrier, no flag).
+ *   y            this rank's plain output [rows_x][y_row_stride]; on completion columns [0, n_peers * w_rows) hold the
+ *                FULL output (every rank's shard), 4-byte aligned, even row stride
+ *   xchg_peers   xchg_peers[r] = address, in rank r's memory, of a symmetric exchange buffer of 8-byte words
+ *                [rows_x][n_peers * w_rows / 2] (the same buffer for all ranks of one call; zero before its first use)
+ *   tag          non-zero.  A consumed word is cleared, so a call may reuse the tag of the buffer's previous use (a CUDA
+ *                graph replay re-issues every call with the tag it was captured with)
+ * The epilogue stores the shard as words (tag << 32 | two adjacent outputs) into EVERY rank's exchange buffer with one
+ * 8-byte store each - whoever sees the tag sees the values - and every CTA, before it exits, collects its slice of all
+ * ranks' words from the local buffer (spinning on the tag) into `y`.  When the kernel has completed on a rank the full
+ * output is in that rank's `y`: consumers are ordered by plain stream order, programmatic dependent launch chains stay
+ * intact.  All ranks must issue the same sequence of calls; at least two exchange buffers must alternate.
+ * Values are bit-identical to the single-GPU output of the same kernel.  rows_x: any (4 per pass). */
+int tg_gemm_w4_rm_exchange(void* y, void* const* xchg_peers, int self_rank, uint32_t tag, int n_peers, int64_t y_row_stride,
+                           const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
                            const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
                            int inner_k_tiles, tg_w4_format format, tg_dtype dtype, void* stream);
 

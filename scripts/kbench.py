@@ -20,8 +20,10 @@ def main():
     op = torch.ops.tinygemm.tinygemm_y_f16RM_x_f16RM_w_any4TC
     out = {}
     checks = {}
-    for n in [int(a) for a in sys.argv[1:]] or [4096, 8192, 11008]:
-        k = n
+    gbps = {}
+    for arg in sys.argv[1:] or ["4096", "8192", "11008"]:   # n (square) or NxK
+        n, k = (int(v) for v in arg.split("x")) if "x" in arg else (int(arg), int(arg))
+        tag = arg
         nbytes = algorithmic_bytes(n, k)
         copies = max(3, int(float(os.environ.get('KB_L2X', '2.6')) * 126e6 / nbytes) + 1)
         layers = [synth_layer(n, k, 10 + i, dev) for i in range(copies)]
@@ -48,7 +50,7 @@ def main():
         ok = all(torch.equal(a, b) for a, b in zip(outs, step()))
         tgf.set_static_weights(os.environ.get('KB_STATIC', '1') == '1')
         _native_lib.tg_set_option(0, int(os.environ.get('KB_PDL', '1')))
-        checks[n] = ok
+        checks[tag] = ok
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
@@ -56,11 +58,12 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / (10 * copies)
-        out[n] = round(us, 2)
+        out[tag] = round(us, 2)
+        gbps[tag] = round(nbytes / us / 1e3)
         del layers, outs, g
         torch.cuda.empty_cache()
     print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("TG_W4")}, "side": os.environ.get("KB_SIDE", "B"), "m": int(os.environ.get("KB_M", "1")), "l2x": os.environ.get("KB_L2X", "2.6"), "us_per_gemv": out, "bit_equal_to_plain_launches": checks,
-                      "GBps": {n: round(algorithmic_bytes(n, n) / us / 1e3) for n, us in out.items()}}))
+                      "GBps": gbps}))
 
 
 if __name__ == "__main__":

@@ -212,3 +212,38 @@ def test_tcgen05_kernel_agrees_with_mma_sync_kernel(fmt, m):
     assert got.shape == ref.shape
     assert ((got.float() - ref.float()).abs() <= 2.0 ** -7 * ref.float().abs() + 1e-3).all()
     assert (got == ref).float().mean() > 0.9
+
+
+@pytest.mark.parametrize("m", [1, 3])
+def test_graph_replay_with_new_activations(m):
+    """A captured launch is replayed with the launch tag it was captured with: the stream-K fix-up (row blocks shared by
+    several CTAs, partial sums exchanged through tagged workspace words) must never take a PREVIOUS replay's partial
+    for its own.  Replay a graph on changing activations and compare every replay with a plain launch."""
+    import tinygemm  # noqa: F401
+    from any4_b200 import _native
+    from bench import synth_layer
+
+    lib = _native.capi()
+    dev = torch.device("cuda:0")
+    n, k = 2048, 8192                                   # 64 row blocks x 8 stages over 148 CTAs: every row block is split
+    w, lut, sz = synth_layer(n, k, 3, dev)
+    op = torch.ops.tinygemm.tinygemm_y_f16RM_x_f16RM_w_any4TC
+    gen = torch.Generator(device=dev).manual_seed(11 + m)
+    x = torch.randn(m, k, device=dev, generator=gen).bfloat16()
+    try:
+        assert lib.tg_set_option(2, 1) == 0             # the tcgen05 kernel
+        for _ in range(2):
+            op(x, w, 128, sz, lut, True)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            ys = [op(x, w, 128, sz, lut, True) for _ in range(3)]   # back to back: programmatic dependent launches
+        for rep in range(4):
+            x.copy_(torch.randn(m, k, device=dev, generator=gen).bfloat16() * (rep + 1))
+            g.replay()
+            torch.cuda.synchronize()
+            want = op(x, w, 128, sz, lut, True)
+            for y in ys:
+                assert torch.equal(y, want), f"replay {rep}"
+    finally:
+        lib.tg_set_option(2, 0)
