@@ -25,6 +25,7 @@ CAPI_SYMBOLS = (
     "tg_gemm_w4_rm", "tg_gemm_w4_rm_sharded", "tg_gemm_w4_rm_exchange", "tg_gemm_w8_rm", "tg_gemm_w16_rm",
     "tg_gemm_tc_workspace_bytes", "tg_gemm_w4_tc", "tg_gemm_w8_tc", "tg_gemm_w16_tc",
     "tg_dequant_int4",
+    "tg_quantize_any4_rows",
     "tg_decode_add_rmsnorm", "tg_decode_silu_mul", "tg_decode_rope_attention", "tg_gemm_w4_rm_silu_pairs",
 )
 
@@ -63,6 +64,8 @@ def capi():
     if hasattr(lib, "tg_gemm_w4_rm_exchange"):
         u32 = ctypes.c_uint32
         lib.tg_gemm_w4_rm_exchange.argtypes = [vp, vp, i32, u32, i32, i64, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
+    if hasattr(lib, "tg_quantize_any4_rows"):
+        lib.tg_quantize_any4_rows.argtypes = [vp, vp, i64, i64, i32, i32, i32, ctypes.c_float, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.tg_gemm_w8_rm.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
     lib.tg_gemm_w16_rm.argtypes = [vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
     lib.tg_gemm_tc_workspace_bytes.argtypes = [i64, i64, i64]

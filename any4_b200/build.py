@@ -26,7 +26,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 
-KERNEL_SOURCES = ["capi.cu", "convert.cu", "gemv_w4_b.cu", "gemv_w4_tc.cu", "gemv_w4_a.cu", "gemv_generic.cu", "decode_ops.cu"]
+KERNEL_SOURCES = ["capi.cu", "convert.cu", "gemv_w4_b.cu", "gemv_w4_tc.cu", "gemv_w4_a.cu", "gemv_generic.cu", "decode_ops.cu", "quantize.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -44,6 +44,9 @@ static bool use_mma_sync_b(int64_t rows_x, int64_t w_rows, int64_t k) {
   if (mode == 2) return true;
   return rows_x == 1 && k <= 4096 && div_up(w_rows, 32) <= 148;
 }
+int launch_quantize_any4_rows(const void* w, const float* sample_weight, int64_t n, int64_t k, int group, int inner_k_tiles,
+                              int max_iter, float tol, int32_t* codes, int32_t* packed, void* sz, void* any4, void* lut,
+                              int* iters, tg_dtype dt, cudaStream_t st);
 int launch_gemm_w4_rm_A(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
                         const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
                         tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st);
@@ -237,6 +240,25 @@ int tg_gemm_w4_rm_exchange(void* y, void* const* xchg_peers, int self_rank, uint
   TG_REQUIRE(tag != 0u, "%s: the call tag must not be 0", fn);
   return gemm_w4_rm_sharded_impl(fn, y, xchg_peers, self_rank, tag, n_peers, y_row_stride, x, w, scales_zeros, lut,
                                  exponents, rows_x, w_rows, k, group, inner_k_tiles, format, dtype, stream);
+}
+
+int tg_quantize_any4_rows(const void* w, const float* sample_weight, int64_t n, int64_t k, int group, int inner_k_tiles,
+                          int max_iter, float tol, int32_t* codes, int32_t* packed, void* scales_zeros, void* any4, void* lut,
+                          int32_t* iters, tg_dtype dtype, void* stream) {
+  const char* fn = "tg_quantize_any4_rows";
+  TG_REQUIRE(w && scales_zeros && any4 && lut, "%s: null tensor pointer", fn);
+  TG_REQUIRE(dtype == TG_BF16 || dtype == TG_FP16, "%s: dtype must be bf16 or fp16", fn);
+  TG_REQUIRE(n > 0 && k > 0 && n < (1ll << 30), "%s: bad sizes n=%lld k=%lld", fn, (long long)n, (long long)k);
+  TG_REQUIRE(valid_group(group) && k % group == 0, "%s: group size must be 32, 64, 128 or 256 and divide k", fn);
+  TG_REQUIRE(k * 5 <= 227 * 1024, "%s: k = %lld does not fit the per-row shared-memory working set (k <= 46489)", fn,
+             (long long)k);
+  TG_REQUIRE(max_iter >= 1 && tol >= 0.f, "%s: bad max_iter / tol", fn);
+  if (packed != nullptr) {
+    TG_REQUIRE(inner_k_tiles == 2 || inner_k_tiles == 4 || inner_k_tiles == 8, "%s: B-layout innerKTiles must be 2, 4 or 8", fn);
+    TG_REQUIRE(n % 8 == 0 && k % 32 == 0, "%s: the packed layout needs n %% 8 == 0 and k %% 32 == 0", fn);
+  }
+  return launch_quantize_any4_rows(w, sample_weight, n, k, group, inner_k_tiles, max_iter, tol, codes, packed, scales_zeros,
+                                   any4, lut, iters, dtype, (cudaStream_t)stream);
 }
 
 int tg_gemm_w4_rm_silu_pairs(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,

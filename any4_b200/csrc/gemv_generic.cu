@@ -273,7 +273,10 @@ __device__ __forceinline__ uint32_t decode8_pair(uint32_t two, uint32_t s2, uint
 //   B layout (weight on the right): B operand = 16 k x 8 weight rows,  A operand = activations (16 rows x k)
 // fp32 accumulation of exact products, as in the reference.  HI: activation rows 8..15 of a pass exist (B layout).
 template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK, bool HI>
-__global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const GParams p, int rows_per_pass, int kpad) {
+#ifndef TG_STREAM_MINB
+#define TG_STREAM_MINB 3  // 78 registers: three CTAs per SM (measured: int8 m = 1 14.4 -> 13.4 us, m = 16 53 -> 37 us at 4096^2)
+#endif
+__global__ void __launch_bounds__(kThreads, TG_STREAM_MINB) gemm_stream_kernel(const GParams p, int rows_per_pass, int kpad) {
   static_assert(KIND != W4, "4-bit weights have their own kernels");
   static_assert(!(ALAYOUT && HI), "the A layout carries at most 8 activation rows per mma");
   constexpr int ROWS = ALAYOUT ? 16 : 8;

@@ -3,8 +3,9 @@
 (`weight` int32, `scales_and_zeros` [k/g][n][2], `lut`, `bias`), `kernel` strings, `w_inner_k`
 semantics, `reshape_weight()` and `forward()`; state_dicts are interchangeable.
 
-Added on top: `RowShardedLinear`, the row-wise multi-GPU wrapper with one
-all-reduce on the m x n output.
+Added on top: `RowShardedLinear`, the row-wise multi-GPU wrapper; `NF4Linear` / `FP4Linear` / `MX4Linear`
+(the reference's TODO, modules.py:10); a checkpoint format that remembers how the weight was packed
+(8(f)-4: extra state `weight_reshaped` / `w_inner_k` / `kernel`).
 """
 import torch
 
@@ -13,7 +14,49 @@ from . import functional as F
 _ops = torch.ops.tinygemm
 
 
-class _PackedLinear(torch.nn.Module):
+class _PackedCheckpoint:
+    """Mixin of the packed-weight modules: the checkpoint format."""
+
+    # ---- checkpoint format (SURVEY.md 8(f)-4) ----
+    # The reference keeps `weight_reshaped`, `w_inner_k` and `kernel` as plain attributes (modules.py:194): a saved
+    # state_dict of a packed model cannot be loaded back, the shape of `weight` alone does not say how it was packed.
+    # Here they travel as the module's extra state, and loading adopts the checkpoint's `weight` / `lut` shapes, so a
+    # packed model reloads without re-packing.  Reference checkpoints (no extra state) still load: the flags keep
+    # their constructor values.
+    _EXTRA_KEYS = ("weight_reshaped", "w_inner_k", "kernel", "group_size")
+
+    def get_extra_state(self):
+        st = {k: getattr(self, k) for k in self._EXTRA_KEYS}
+        st["format"] = "any4_b200/1"
+        return st
+
+    def set_extra_state(self, state):
+        if not state:
+            return
+        for k in self._EXTRA_KEYS:
+            if k in state:
+                setattr(self, k, state[k])
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        for name in ("weight", "lut", "exponents"):
+            t = state_dict.get(prefix + name)
+            cur = getattr(self, name, None)
+            if t is not None and cur is not None and t.shape != cur.shape:
+                # packed (4-D) vs unpacked ([out][in]) weight, per-row vs global LUT: take the checkpoint's layout
+                setattr(self, name, torch.nn.Parameter(torch.empty(t.shape, device=cur.device, dtype=cur.dtype),
+                                                       requires_grad=cur.requires_grad))
+        n_missing = len(missing_keys)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+        extra = prefix + torch.nn.modules.module._EXTRA_STATE_KEY_SUFFIX
+        if extra in missing_keys[n_missing:]:
+            missing_keys.remove(extra)  # a reference checkpoint: flags stay as constructed ...
+            if self.weight.dim() == 4:  # ... except that a 4-D weight can only be a packed one
+                layout = getattr(self, "_PACKERS", {}).get(self.kernel, "Bint4")
+                per_ik = {"Bint4": 0.5, "Aint4": 1, "Bint8": 1, "Aint8": 2}[layout]  # last dim = inner_k * this
+                self.weight_reshaped, self.w_inner_k = True, int(self.weight.shape[3] / per_ik)
+
+
+class _PackedLinear(_PackedCheckpoint, torch.nn.Module):
     """Shared machinery: parameters, weight packing by kernel name, bias, reshape of activations."""
 
     # kernel name -> (convert op suffix used by reshape_weight); None = forward-only kernel
@@ -158,6 +201,117 @@ class Any4Linear(_PackedLinear):
 
     def extra_repr(self):
         return super().extra_repr() + f", per_row={self.per_row}"
+
+
+# The reference leaves these as a TODO (modules.py:10 "add FP4Linear, NF4Linear, MX4Linear").  NF4 and FP4 are any4 with
+# ONE fixed 16-entry table for all rows (value = table[code] * scale + zero, scale = the group's absmax / table max,
+# zero = 0): same kernels, `lut` is a buffer instead of a learnt parameter.  MX4 (OCP microscaling: fp4 e2m1 codes, one
+# shared power-of-two exponent per 32 weights) runs through the mx4 op.
+NF4_TABLE = (-1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453, -0.28444138169288635,
+             -0.18477343022823334, -0.09105003625154495, 0.0, 0.07958029955625534, 0.16093020141124725,
+             0.24611230194568634, 0.33791524171829224, 0.44070982933044434, 0.5626170039176941, 0.7229568362236023, 1.0)
+FP4_TABLE = (0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0, -0.0, -0.5, -1.0, -1.5, -2.0, -3.0, -4.0, -6.0)  # e2m1, sign = bit 3
+
+
+class _FixedTableLinear(Any4Linear):
+    """any4 with a fixed global table.  `quantize_weight(w)` fills codes / scales from a float weight (absmax scaling
+    per group, nearest table entry) and packs them."""
+
+    TABLE = None
+
+    def __init__(self, in_features, out_features, bias=True, device=None, dtype=None, group_size=128,
+                 kernel="linear_y_f16RM_x_f16RM_W_any4TC", w_inner_k=4):
+        super().__init__(in_features, out_features, bias, device, dtype, group_size, kernel, w_inner_k, per_row=False)
+
+    def _init_extra(self, device, dtype):
+        # a Parameter, as in Any4Linear (the kernels read `self.lut`; state_dicts stay loadable into Any4Linear)
+        self.lut = torch.nn.Parameter(torch.tensor(self.TABLE, device=device, dtype=dtype), requires_grad=False)
+
+    @torch.no_grad()
+    def quantize_weight(self, w, w_inner_k=None):
+        n, k, g = self.out_features, self.in_features, self.group_size
+        if tuple(w.shape) != (n, k):
+            raise ValueError(f"expected a [{n}][{k}] weight")
+        dt = self.scales_and_zeros.dtype
+        table = torch.tensor(self.TABLE, device=w.device, dtype=torch.float32)
+        wg = w.float().view(n, k // g, g)
+        scale = (wg.abs().amax(-1) / table.abs().max()).clamp_min(1e-8).to(dt)            # [n][k/g], rounded as stored
+        codes = ((wg / scale.float().unsqueeze(-1)).unsqueeze(-1) - table).abs().argmin(-1)  # nearest table entry
+        self.weight = torch.nn.Parameter(codes.view(n, k).to(torch.int32).to(self.weight.device), requires_grad=False)
+        sz = torch.stack([scale.t(), torch.zeros_like(scale.t())], 2).contiguous()           # [k/g][n][2]
+        self.scales_and_zeros.data = sz.to(self.scales_and_zeros.device)
+        self.weight_reshaped = False
+        self.reshape_weight(w_inner_k)
+        return self
+
+
+class NF4Linear(_FixedTableLinear):
+    """QLoRA NormalFloat4 (the table of kmeans.py:17 in the reference) through the any4 kernels."""
+    TABLE = NF4_TABLE
+
+
+class FP4Linear(_FixedTableLinear):
+    """fp4 e2m1 values with a real-valued group scale through the any4 kernels."""
+    TABLE = FP4_TABLE
+
+
+class MX4Linear(_PackedCheckpoint, torch.nn.Module):
+    """OCP MX fp4 (e2m1 codes + one e8m0 exponent per 32 weights, tinygemm_lib/utils.py:137-232) through
+    `tinygemm_y_f16RM_x_f16RM_w_mx4TC`; bf16 activations only, as the reference op.  Parameters: `weight` int32 codes
+    ([out][in], or the packed B int4 layout after `reshape_weight`), `exponents` uint8 [out][in / 32], `bias`."""
+
+    GROUP = 32
+
+    def __init__(self, in_features, out_features, bias=True, device=None, dtype=torch.bfloat16, w_inner_k=4):
+        super().__init__()
+        if dtype not in (None, torch.bfloat16):
+            raise ValueError("MX4Linear: the mx4 kernels take bfloat16 activations only")
+        if in_features % self.GROUP:
+            raise ValueError("MX4Linear: in_features must be a multiple of 32")
+        self.in_features, self.out_features, self.group_size = in_features, out_features, self.GROUP
+        self.weight = torch.nn.Parameter(torch.zeros((out_features, in_features), device=device, dtype=torch.int32),
+                                         requires_grad=False)
+        self.exponents = torch.nn.Parameter(torch.full((out_features, in_features // self.GROUP), 127, device=device,
+                                                       dtype=torch.uint8), requires_grad=False)
+        if bias:
+            self.bias = torch.nn.Parameter(torch.empty(out_features, device=device, dtype=torch.bfloat16))
+        else:
+            self.register_parameter("bias", None)
+        self.kernel = "tinygemm_y_f16RM_x_f16RM_w_mx4TC"
+        self.w_inner_k = w_inner_k
+        self.weight_reshaped = False
+
+    def reshape_weight(self, w_inner_k=None):
+        w_inner_k = self.w_inner_k if w_inner_k is None else w_inner_k
+        self.weight.data = _ops.convert_matrix_to_m16n8k16_Bint4_layout(self.weight, w_inner_k)
+        self.weight_reshaped, self.w_inner_k = True, w_inner_k
+
+    @torch.no_grad()
+    def quantize_weight(self, w, w_inner_k=None):
+        from . import utils as U
+
+        if tuple(w.shape) != (self.out_features, self.in_features):
+            raise ValueError(f"expected a [{self.out_features}][{self.in_features}] weight")
+        codes, exps = U.quantize_mx4(w.to(torch.bfloat16), self.GROUP)
+        self.weight = torch.nn.Parameter(codes.to(torch.int32).to(self.weight.device), requires_grad=False)
+        self.exponents = torch.nn.Parameter(exps.to(torch.uint8).to(self.exponents.device), requires_grad=False)
+        self.weight_reshaped = False
+        self.reshape_weight(w_inner_k)
+        return self
+
+    def forward(self, input):
+        if not self.weight_reshaped:
+            raise RuntimeError("MX4Linear: pack the weight first (reshape_weight / quantize_weight)")
+        lead = input.shape[:-1]
+        y = _ops.tinygemm_y_f16RM_x_f16RM_w_mx4TC(input.view(-1, input.shape[-1]), self.weight, self.GROUP,
+                                                   self.exponents, True)
+        y = y[:, : self.out_features]
+        if self.bias is not None:
+            y = y + self.bias
+        return y.reshape(*lead, self.out_features)
+
+    def extra_repr(self):
+        return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}, group_size=32"
 
 
 def fuse_rows(linears, interleave=False):

@@ -52,8 +52,9 @@ def measured_peak():
 
 def ncu_traffic():
     """DRAM bytes per launch of the headline kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
-    `ncu --set full` capture of this same kernel and shape (profiles/r1/ncu_prof_summary.txt); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r1", "ncu_prof_summary.txt")
+    `ncu --set full` capture of this same kernel and shape taken in this round's GPU run (profiles/r2/ncu_b4096.txt, stamped
+    with the commit it was taken at); None if absent.  (ncu cannot run inside the timed bench: a profiled run is never timed.)"""
+    path = os.path.join(ROOT, "profiles", "r2", "ncu_b4096.txt")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     try:
         tot = 0.0
@@ -378,8 +379,36 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     head = bench_shape(HEADLINE, HEADLINE, args.steps, args.warmup, True)
     extra = [bench_shape(s, s, max(3, args.steps // 2), args.warmup, False) for s in EXTRA_SHAPES]
+    # the same headline measurement with the library's DEFAULT options (weights not declared static: the whole kernel,
+    # not only its activation staging, is ordered behind the previous kernel of the stream)
+    tgf.set_static_weights(False)
+    head_default = bench_shape(HEADLINE, HEADLINE, max(3, args.steps // 2), args.warmup, False)
+    tgf.set_static_weights(True)
     clocks = sampler.stop() if sampler else None
     sweep = format_sweep() if (rank == 0 and world == 1 and not args.no_sweep) else None
+
+    # BASELINE.json's second metric (configs[2] / configs[4]): Llama-3-8B any4 g=128 single-token decode on this
+    # many GPUs, one CUDA graph per token, row-sharded with the in-kernel exchange when N > 1 (bench_llama.py)
+    llama = None
+    if not args.no_llama:
+        import bench_llama
+
+        llama = {}
+        for lm_head in ("bf16", "any4"):
+            r = bench_llama.run_decode(dev, rank, world, dist, steps=args.llama_steps, warmup=3, exchange=args.exchange,
+                                       lm_head_any4=lm_head == "any4", lib=lib)
+            if rank == 0:
+                llama["lm_head_" + lm_head] = {
+                    "tok_s": round(r["value"], 1), "ms_per_token": round(r["ms_per_token"], 4),
+                    "bytes_per_token_per_gpu": int(r["bytes_per_token_per_gpu"]),
+                    "frac_of_hbm_bound": round(r["roofline"]["frac"], 4),
+                    "library_launches_per_token": r["library_launches_per_token"]}
+                llama.setdefault("workload", r["config"]["workload"])
+                llama.setdefault("plumbing", r["config"]["plumbing"])
+                llama.setdefault("parallelism", r["config"]["parallelism"])
+        if rank == 0:
+            llama["note"] = ("lm_head_bf16 = the reference's configuration (quantize.py:34-36 leaves lm_head unquantized, "
+                             "cuBLAS GEMV); lm_head_any4 = lm_head through the same any4 kernel (SURVEY 8f-3)")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -407,8 +436,11 @@ def run_ours(args):
                 "l2_policy": f"inputs larger than L2: {head['copies']} distinct weight sets = "
                              f"{head['copies'] * nbytes / 1e6:.0f} MB rotated every step",
                 "parallelism": "1 GPU" if world == 1 else (
-                    f"row-sharded x{world}, exchange fused into the GEMV epilogue (peer stores over NVLink, completion counter in symmetric memory, no barrier / collective launch)"
+                    f"row-sharded x{world}, exchange inside the GEMV (tagged 8-byte words stored into every rank's symmetric buffer over NVLink, collected before the kernel exits; no barrier / collective launch)"
                     if args.exchange == "fused" else f"row-sharded x{world} + NCCL all-reduce on y"),
+                "options": "TG_OPT_STATIC_WEIGHTS = 1 (weights / LUT / scales of a loaded model never change between launches)",
+                "default_options": {"GBps": round(head_default["gbps"], 1), "us_per_gemv": round(head_default["us_per_gemv"], 3),
+                                    "frac_of_peak": round(head_default["gbps"] / world / peak, 4)},
                 "other_shapes": {f"{e['n']}x{e['k']}": {"GBps": round(e["gbps"], 1), "us_per_gemv": round(e["us_per_gemv"], 3),
                                                          "frac_of_peak": round(e["gbps"] / world / peak, 4)} for e in extra},
             },
@@ -427,6 +459,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if sweep is not None:
             line["config"]["format_sweep_us"] = sweep
+        if llama is not None:
+            line["config"]["llama_decode"] = llama
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -444,6 +478,8 @@ def main():
                     help="N > 1: 'fused' = GEMV epilogue stores into all ranks' symmetric buffers + one barrier; "
                          "'nccl' = zero-padded all-reduce")
     ap.add_argument("--no-sweep", action="store_true", help="skip the informational format / m sweep")
+    ap.add_argument("--no-llama", action="store_true", help="skip the Llama-3-8B decode measurement")
+    ap.add_argument("--llama-steps", type=int, default=30, help="timed decode steps (CUDA-graph replays) per variant")
     ap.add_argument("--profile-shape", type=int, default=0, help="(for ncu) run only the n=k=N GEMV set")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

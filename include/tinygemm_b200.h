@@ -213,6 +213,21 @@ int tg_gemm_w16_tc(void* y, const void* x, const void* w, int64_t rows_x, int64_
 int tg_dequant_int4(const int32_t* in, void* out, int64_t n_words, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * any4 quantizer front-end: one kernel, one CTA per weight row.  Replaces the reference's CPU
+ * pipeline group_q (quantize.py:106-149) -> cluster_matrix / cluster_row (quantize.py:433-521) -> kmeans.run_kmeans
+ * (kmeans.py:200-262, init "int" = kmeans.py:41-46) -> lut = any4 - 8 (quantize.py:893) ->
+ * convert_matrix_to_m16n8k16_Bint4_layout, for 4 bit, per-row LUT, asymmetric groups with zero point.
+ *   w              [n][k] dtype, row-major              sample_weight  [k] fp32 or NULL (weighted k-means)
+ *   codes          [n][k] int32 or NULL                 packed         B int4 layout [n/8][k/(ik*16)][32][ik/2] or NULL
+ *   scales_zeros   [k/group][n][2] dtype                any4           [n][16] dtype, centroids in [0, 15] code space
+ *   lut            [n][16] dtype = any4 - 8 (what the GEMV takes)       iters  [n] int32 Lloyd iterations run, or NULL
+ * Group statistics and the stored scale / zero are the reference's fp32 operations (bit-identical); Lloyd's sums are
+ * fp32 in a fixed order (deterministic, not numpy's: a value within an ulp of a boundary may take the other code). */
+int tg_quantize_any4_rows(const void* w, const float* sample_weight, int64_t n, int64_t k, int group, int inner_k_tiles,
+                          int max_iter, float tol, int32_t* codes, int32_t* packed, void* scales_zeros, void* any4, void* lut,
+                          int32_t* iters, tg_dtype dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Decode-step plumbing around the GEMVs (no counterpart in tinygemm_lib - the
  * reference leaves these to the HF model code its benchmark.py:145-146 times as a whole).  Single token,
  * dtype = activation dtype, all kernels use programmatic dependent launch like the GEMVs (TG_OPT_PDL).

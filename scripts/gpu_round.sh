@@ -17,7 +17,7 @@ if [ "${REFBENCH:-0}" = "1" ]; then
 for s in 4096 8192 11008; do timeout 300 python oracle/ref_runner.py bench $s $s 10 >> gpurun_out/ref_gpu_bench.jsonl 2>> gpurun_out/ref_gpu_bench.err; done; cat gpurun_out/ref_gpu_bench.jsonl
 fi
 if [ "${NCU:-0}" = "1" ]; then
-echo "== ncu launches"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemv_w4_b|gemm_frag|_kernel" -s 300 -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph --no-sweep > gpurun_out/ncu_bench.log 2>&1; echo "ncu1 rc=$?"
+echo "== ncu launches"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemv_w4_b|gemm_frag|_kernel" -s 300 -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph --no-sweep --no-llama > gpurun_out/ncu_bench.log 2>&1; echo "ncu1 rc=$?"
 echo "== ncu full 8192"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemv_w4_b -s 12 -c 2 -o gpurun_out/prof8192 python bench.py --steps 2 --warmup 3 --no-graph --profile-shape 8192 > gpurun_out/ncu_full8192.log 2>&1; echo "ncu3 rc=$?"
 echo "== ncu full"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemv_w4_b -s 60 -c 3 -o gpurun_out/prof python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph --no-sweep > gpurun_out/ncu_full.log 2>&1; echo "ncu2 rc=$?"
 fi

@@ -247,3 +247,24 @@ def test_graph_replay_with_new_activations(m):
                 assert torch.equal(y, want), f"replay {rep}"
     finally:
         lib.tg_set_option(2, 0)
+
+
+@pytest.mark.parametrize("api", ["linear_y_f16RM_W_int4TC_x_f16RM", "linear_y_f16RM_W_int8TC_x_f16RM"])
+def test_reference_general_mul_case_against_fp32(api):
+    """The reference's `test_general_mul` cases that fail on a B200 for the reference's OWN kernels as well as for ours
+    (profiles/r2/reference_testsuite_*.txt; weight in {0, 1} on the left, 3 activation rows, k = 2048): they compare
+    with a bf16 cuBLAS product whose error alone is at the 0.1 threshold.  Against the fp32 product of the same
+    operands the kernels' average error is two orders of magnitude below it."""
+    import tinygemm_lib.functional as TF
+    from tinygemm_lib.utils import group_quantize_tensor
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(3)
+    for (m, n, k, ik, g) in [(32, 3, 2048, 2, 64), (48, 3, 2048, 2, 256), (32, 3, 2048, 2, 128)]:
+        w = torch.randint(0, 2, (m, k), device=dev, generator=gen).bfloat16()
+        x = torch.randn(n, k, device=dev, generator=gen).bfloat16()
+        codes, sz = group_quantize_tensor(w, n_bit=8 if "int8" in api else 4, q_group_size=g)
+        y = getattr(TF, api)(x, codes, sz, g, ik)
+        exact = (w.float() @ x.float().t()).t()
+        avg_err = float((exact - y[:, :m].float()).abs().sum() / (m * n))
+        assert avg_err < 5e-2, (api, m, n, k, avg_err)   # bf16 rounding of |y| ~ 30: half an ulp = 0.06 at most, ~0.03 on average

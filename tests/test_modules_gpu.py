@@ -91,3 +91,53 @@ def test_row_sharded_linear_single_process(cuda_device):
         parts.append(sh(x))
     total = parts[0] + parts[1] + m.bias
     assert torch.equal(total, y)
+
+
+@pytest.mark.parametrize("cls_name", ["NF4Linear", "FP4Linear"])
+def test_fixed_table_linear(cls_name, cuda_device):
+    """NF4 / FP4 module shells (the reference's TODO, modules.py:10): quantize a float weight, run through the any4
+    kernel with the fixed global table, compare with the CPU dequantisation of the stored codes / scales."""
+    import any4_b200.modules as M
+
+    gen = torch.Generator().manual_seed(4)
+    w = torch.randn(128, 512, generator=gen) * 0.05
+    x = torch.randn(3, 512, generator=gen).bfloat16()
+    lin = getattr(M, cls_name)(512, 128, bias=False, device=cuda_device, dtype=torch.bfloat16, group_size=64)
+    lin.quantize_weight(w.to(cuda_device))
+    assert lin.weight_reshaped and lin.weight.dim() == 4
+    y = lin(x.to(cuda_device))
+    # the same quantisation on the CPU, dequantised by the oracle
+    ref_lin = getattr(M, cls_name)(512, 128, bias=False, device="cpu", dtype=torch.bfloat16, group_size=64)
+    table = torch.tensor(ref_lin.TABLE)
+    wg = w.view(128, 8, 64)
+    scale = (wg.abs().amax(-1) / table.abs().max()).clamp_min(1e-8).bfloat16()
+    codes = ((wg / scale.float().unsqueeze(-1)).unsqueeze(-1) - table).abs().argmin(-1).view(128, 512)
+    sz = torch.stack([scale.t(), torch.zeros_like(scale.t())], 2).contiguous()
+    wd = dequant.dequant_lut(codes, table.bfloat16(), sz, 64, torch.bfloat16)
+    assert _tol.frob_rel(y.cpu(), dequant.gemm(x, wd)) <= _tol.FROB_REL
+    # and the quantised layer approximates the float one (4-bit: a few percent)
+    full = (x.float() @ w.t()).bfloat16()
+    assert _tol.frob_rel(y.cpu(), full) < 0.2
+
+
+def test_mx4_linear_and_checkpoint(cuda_device):
+    """MX4Linear against dequantize_mx4 + matmul, then a packed checkpoint round trip: the reloaded layer needs no
+    re-packing and gives the same bits."""
+    from any4_b200 import utils as host
+    from any4_b200.modules import MX4Linear
+
+    gen = torch.Generator().manual_seed(5)
+    w = (torch.randn(64, 256, generator=gen) * 0.1).bfloat16()
+    x = torch.randn(4, 256, generator=gen).bfloat16()
+    lin = MX4Linear(256, 64, bias=True, device=cuda_device)
+    lin.bias.data = torch.randn(64, generator=gen).bfloat16().to(cuda_device)
+    lin.quantize_weight(w.to(cuda_device))
+    y = lin(x.to(cuda_device))
+    codes, exps = host.quantize_mx4(w, 32)
+    wd = host.dequantize_mx4(codes, exps).to(torch.bfloat16)
+    ref = (dequant.gemm(x, wd).float() + lin.bias.data.cpu().float()).bfloat16()
+    assert y.shape == (4, 64) and _tol.frob_rel(y.cpu(), ref) <= 2e-3
+    fresh = MX4Linear(256, 64, bias=True, device=cuda_device)
+    fresh.load_state_dict(lin.state_dict())
+    assert fresh.weight_reshaped and fresh.weight.dim() == 4
+    assert torch.equal(fresh(x.to(cuda_device)), y)
