@@ -265,6 +265,6 @@ def test_reference_general_mul_case_against_fp32(api):
         x = torch.randn(n, k, device=dev, generator=gen).bfloat16()
         codes, sz = group_quantize_tensor(w, n_bit=8 if "int8" in api else 4, q_group_size=g)
         y = getattr(TF, api)(x, codes, sz, g, ik)
-        exact = (w.float() @ x.float().t()).t()
-        avg_err = float((exact - y[:, :m].float()).abs().sum() / (m * n))
-        assert avg_err < 5e-2, (api, m, n, k, avg_err)   # bf16 rounding of |y| ~ 30: half an ulp = 0.06 at most, ~0.03 on average
+        exact = (w.float() @ x.float().t()).t().bfloat16()  # the fp32 product, rounded once (weights 0 / 1 dequantise exactly)
+        avg_err = float((exact.float() - y[:, :m].float()).abs().sum() / (m * n))
+        assert avg_err < 1e-2, (api, m, n, k, avg_err)

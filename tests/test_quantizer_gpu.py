@@ -69,14 +69,16 @@ def test_any4_linear_from_float(cuda_device):
     q = any4_linear_from_float(lin, group_size=128)
     assert q.weight_reshaped and q.weight.shape == (32, 16, 32, 2) and q.lut.shape == (256, 16)
     x = torch.randn(5, 1024, generator=gen).bfloat16().to(cuda_device)
-    y, want = q(x).float(), lin(x).float()
+    with torch.no_grad():
+        y, want = q(x).float(), lin(x).float()
     rel = float((y - want).norm() / want.norm())
-    assert rel < 0.08, rel                                                 # 4-bit any4: a few percent
+    assert rel < 0.12, rel            # 16 optimal levels on Gaussian weights: ~0.1 relative (Lloyd-Max: MSE = 0.0095 sigma^2)
     # and better than plain int4 with the same groups
     from any4_b200 import utils as U
     codes, sz = U.group_quantize_tensor(lin.weight.data, 4, 128)
     wi = ((codes.float() - 8) * sz[..., 0].t().float().repeat_interleave(128, 1) + sz[..., 1].t().float().repeat_interleave(128, 1))
-    rel_int4 = float((x.float() @ wi.t() + lin.bias.float() - want).norm() / want.norm())
+    with torch.no_grad():
+        rel_int4 = float((x.float() @ wi.t() + lin.bias.float() - want).norm() / want.norm())
     assert rel < rel_int4
 
 
