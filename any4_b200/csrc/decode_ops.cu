@@ -277,6 +277,20 @@ rope_attn_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ 
   out[(size_t)h * kHeadDim + d] = Cvt<T>::r(o * inv);
 }
 
+// ---------------------------------------------------------------------------------------
+// host activations -> device staging buffer (tg_gemm_w4_rm_hostio): 16-byte pieces straight out of pinned host memory
+// (unified addressing).  One CTA: the 8 KB of a decode step are latency, not bandwidth; the dependent GEMV (static
+// weights) streams its weights and fills its first tensor-memory slots while these loads cross PCIe.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) stage_host_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n16) {
+  pdl_prologue();
+  for (int i = (int)threadIdx.x; i < n16; i += 256) {
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
+    dst[i] = v;
+  }
+}
+
 template <typename... KArgs, typename... Args>
 int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, const char* what, Args... args) {
   cudaLaunchConfig_t cfg{};
@@ -350,4 +364,21 @@ extern "C" int tg_decode_rope_attention(const void* qkv, const void* cos, const 
   return launch_pdl(rope_attn_kernel<__half>, dim3(n_heads), dim3(kHeadDim), st, fn, (const uint16_t*)qkv,
                     (const uint16_t*)cos, (const uint16_t*)sin, (uint16_t*)k_cache, (uint16_t*)v_cache, (uint16_t*)out,
                     n_heads, n_kv_heads, pos, cache_len, scale);
+}
+
+extern "C" int tg_gemm_w4_rm_hostio(void* y_host, const void* x_host, void* x_staging, const int32_t* w,
+                                    const void* scales_zeros, const void* lut, const uint8_t* exponents, int64_t rows_x,
+                                    int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_w4_format format,
+                                    tg_weight_side side, tg_dtype dtype, void* stream) {
+  const char* fn = "tg_gemm_w4_rm_hostio";
+  TG_REQUIRE(y_host && x_host && x_staging, "%s: null pointer", fn);
+  TG_REQUIRE(rows_x >= 1 && k > 0 && (rows_x * k) % 8 == 0 && rows_x * k * 2 <= (1ll << 20),
+             "%s: the activations (rows_x * k) must be a multiple of 8 elements and at most 1 MiB", fn);
+  TG_REQUIRE(((reinterpret_cast<uintptr_t>(x_host) | reinterpret_cast<uintptr_t>(x_staging)) & 15u) == 0,
+             "%s: x_host and x_staging must be 16-byte aligned", fn);
+  int rc = launch_pdl(stage_host_kernel, dim3(1), dim3(256), (cudaStream_t)stream, fn, (const uint4*)x_host,
+                      (uint4*)x_staging, (int)(rows_x * k / 8));
+  if (rc != TG_OK) return rc;
+  return tg_gemm_w4_rm(y_host, x_staging, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, inner_k_tiles, format,
+                       side, dtype, stream);
 }

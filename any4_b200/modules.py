@@ -199,6 +199,61 @@ class Any4Linear(_PackedLinear):
         return fn(x2d, self.weight, self.lut, self.scales_and_zeros, self.group_size, w_inner_k=self.w_inner_k,
                   reshape_weight=not self.weight_reshaped)
 
+    def bind_host(self, input, out=None):
+        """Decode step for HOST activations (include/tinygemm_b200.h: tg_gemm_w4_rm_hostio).  `input`: pinned CPU tensor
+        [m][in_features] (m small); `out`: pinned CPU tensor [m][padded out_features] (allocated if None).  Returns
+        (launch, out): `launch()` enqueues, on the current stream of the weight's device, a one-CTA kernel that pulls the
+        activations out of pinned host memory into a private staging buffer and the GEMV kernel, which writes its
+        outputs straight into the pinned host buffer - no copy-engine transfers, no output staging; the GEMV's weight
+        stream runs while the activations cross PCIe.  (They are staged because every CTA reads all of them: from the
+        device they come out of L2, from host memory each read would cross PCIe.)  All argument checks happen here,
+        once.  Synchronize the stream before reading `out`; refill `input` in place between launches.
+        Weight-on-the-right kernel, packed weight, no bias."""
+        import ctypes
+
+        from . import _native
+
+        if self.kernel != "linear_y_f16RM_x_f16RM_W_any4TC" or not self.weight_reshaped or self.bias is not None:
+            raise RuntimeError("bind_host needs a packed weight-on-the-right any4 layer without bias")
+        dt = self.scales_and_zeros.dtype
+        if input.is_cuda or not input.is_pinned() or input.dtype != dt or not input.is_contiguous():
+            raise RuntimeError(f"bind_host: input must be a contiguous pinned CPU tensor of dtype {dt}")
+        x2d = input.view(-1, input.shape[-1])
+        m, k = x2d.shape
+        w = self.weight
+        w_rows = w.shape[0] * 8
+        if k != self.in_features:
+            raise RuntimeError("bind_host: wrong in_features")
+        if out is None:
+            out = torch.empty((m, w_rows), dtype=dt).pin_memory()
+        if out.is_cuda or not out.is_pinned() or out.dtype != dt or tuple(out.shape) != (m, w_rows) or not out.is_contiguous():
+            raise RuntimeError(f"bind_host: out must be a contiguous pinned CPU tensor [{m}][{w_rows}] of dtype {dt}")
+        fmt = 2 if self.lut.dim() == 2 else 1  # tg_w4_format: any4 row-wise / global
+        fn = _native.capi().tg_gemm_w4_rm_hostio
+        dev = w.device
+        xd = torch.empty((m, k), device=dev, dtype=dt)
+        args = (ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(x2d.data_ptr()), ctypes.c_void_p(xd.data_ptr()),
+                ctypes.c_void_p(w.data_ptr()), ctypes.c_void_p(self.scales_and_zeros.data_ptr()),
+                ctypes.c_void_p(self.lut.data_ptr()), None,
+                m, w_rows, k, self.group_size, w.shape[3] * 2, fmt, 1, 0 if dt == torch.bfloat16 else 1)
+        keep = (input, out, xd, w, self.scales_and_zeros, self.lut)  # the bound buffers live as long as the callable
+        stream_of = torch.cuda.current_stream
+
+        def launch(_keep=keep):
+            if torch.cuda.current_device() != dev.index:
+                raise RuntimeError("bind_host: make the weight's device current before launching")
+            if fn(*args, ctypes.c_void_p(stream_of().cuda_stream)) != 0:
+                raise RuntimeError(_native.last_error())
+
+        return launch, out
+
+    def forward_host(self, input, out=None):
+        """One-shot form of `bind_host`: launch and return `out` (pinned CPU; synchronize before reading it)."""
+        with torch.cuda.device(self.weight.device):
+            launch, out = self.bind_host(input, out)
+            launch()
+        return out
+
     def extra_repr(self):
         return super().extra_repr() + f", per_row={self.per_row}"
 

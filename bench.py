@@ -295,17 +295,35 @@ def run_ours(args):
                "us_per_gemv": ms * 1e3 / (steps * copies),
                "gbps": nbytes * copies * steps / (ms * 1e-3) / 1e9}
         if with_e2e:
+            # end to end through the public module API with HOST buffers: the activations start in pinned host memory
+            # and the outputs must be readable on the host when the step ends (synchronize inside the timed region)
             xh = torch.randn(1, k).bfloat16().pin_memory()
-            yh = torch.empty(1, n, dtype=torch.bfloat16).pin_memory()
-            xd = torch.empty(1, k, device=dev, dtype=torch.bfloat16)
+            if world == 1:
+                # Any4Linear.bind_host: per call a one-CTA kernel pulls x (k * 2 bytes) out of pinned host memory and the
+                # GEMV kernel writes y (n * 2 bytes) straight into the pinned host buffer - no copy-engine transfers
+                bound = [lin.bind_host(xh) for lin in layers]
+                out["e2e_api"] = "Any4Linear.bind_host (tg_gemm_w4_rm_hostio: x pulled from / y written to pinned host memory by the kernels)"
 
-            def step_e2e():
-                for lin in layers:
-                    xd.copy_(xh, non_blocking=True)
-                    yh.copy_(lin(xd), non_blocking=True)
-                torch.cuda.synchronize()
+                def step_e2e():
+                    for launch, _ in bound:
+                        launch()
+                    torch.cuda.synchronize()
+            else:
+                yh = torch.empty(1, n, dtype=torch.bfloat16).pin_memory()
+                xd = torch.empty(1, k, device=dev, dtype=torch.bfloat16)
+                out["e2e_api"] = "RowShardedLinear.forward with explicit pinned-memory copies"
+
+                def step_e2e():
+                    for lin in layers:
+                        xd.copy_(xh, non_blocking=True)
+                        yh.copy_(lin(xd), non_blocking=True)
+                    torch.cuda.synchronize()
 
             ms2 = time_gemv_set(step_e2e, copies, steps, warmup, dist)
+            if world == 1:  # what arrived on the host is the device result, bit for bit
+                xd = xh.to(dev)
+                for (launch, yh_i), lin in zip(bound[:3], layers[:3]):
+                    assert torch.equal(yh_i.to(dev), lin(xd)), "bind_host output differs from the device-resident forward"
             out["e2e_gbps"] = nbytes * copies * steps / (ms2 * 1e-3) / 1e9
             out["h2d"] = copies * k * 2
             out["d2h"] = copies * n * 2
@@ -362,6 +380,9 @@ def run_ours(args):
         wa = [w.view(n // 16, k // 64, 32, 4) for w, _, _ in ws]       # same bytes viewed as the A int4 layout (ik = 4)
         out["m1"]["int4_g128_A_layout(Int4Linear default)"] = timed(
             lambda: [ops.tinygemm_y_f16RM_x_f16RM_w_int4TC(w, x, G, sz, False) for w, (_, _, sz) in zip(wa, ws)])
+        x16 = torch.randn(16, k, device=dev).bfloat16()  # (the A-layout kernel takes one activation row per launch)
+        out["m16"]["int4_g128_A_layout(Int4Linear default)"] = timed(
+            lambda: [ops.tinygemm_y_f16RM_x_f16RM_w_int4TC(w, x16, G, sz, False) for w, (_, _, sz) in zip(wa, ws)])
         # int8 and 16-bit weights (fragment-order kernel, untuned): 8 weight sets are enough to exceed L2 for 16-bit
         w8 = [torch.randint(-2**31, 2**31 - 1, (n // 8, k // 64, 32, 4), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
               for _ in range(16)]
@@ -449,7 +470,7 @@ def run_ours(args):
                          "kernel": "gemv_w4_b_kernel<bf16, ik=4, m=1>", "us_per_launch": us,
                          "algorithmic_bytes_per_launch": per_rank_bytes},
             "e2e": {"value": head["e2e_gbps"], "unit": "GB/s", "h2d_bytes_per_step": head["h2d"],
-                    "d2h_bytes_per_step": head["d2h"]},
+                    "d2h_bytes_per_step": head["d2h"], "api": head.get("e2e_api")},
             "gpu_launches": head["launches"],
             "parity_checked": (parity["ok"] if parity["checked"] else None),
             "parity_frac_bit_equal": parity.get("frac_bit_equal"),

@@ -138,6 +138,15 @@ int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_z
                   const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
                   int inner_k_tiles, tg_w4_format format, tg_weight_side side, tg_dtype dtype, void* stream);
 
+/* The same GEMM for a decode step whose activations live in PINNED HOST memory and whose result is wanted there
+ * (no counterpart in the reference, whose ops take device tensors): one tiny kernel pulls `x_host` (device-accessible
+ * pinned memory, unified addressing) into the device buffer `x_staging` [rows_x][k], the GEMV - ordered behind it by
+ * programmatic dependent launch, its weight stream already running - writes its outputs straight to `y_host`.  Two
+ * kernel launches from ONE call, no copy-engine transfers.  (x is staged because every CTA reads all of it.) */
+int tg_gemm_w4_rm_hostio(void* y_host, const void* x_host, void* x_staging, const int32_t* w, const void* scales_zeros,
+                         const void* lut, const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
+                         int inner_k_tiles, tg_w4_format format, tg_weight_side side, tg_dtype dtype, void* stream);
+
 /* Row-sharded multi-GPU variant of the B-layout 4-bit GEMV with the exchange FUSED into the epilogue (no
  * counterpart in the reference, which is single-GPU).  This rank holds `w_rows` consecutive weight
  * rows of an n-row layer; `y_peers[r]` is the address, in rank r's copy of a symmetric (peer-mapped) m x n output

@@ -141,3 +141,29 @@ def test_mx4_linear_and_checkpoint(cuda_device):
     fresh.load_state_dict(lin.state_dict())
     assert fresh.weight_reshaped and fresh.weight.dim() == 4
     assert torch.equal(fresh(x.to(cuda_device)), y)
+
+
+def test_bind_host_zero_copy(cuda_device):
+    """Any4Linear.bind_host / forward_host: pinned host activations in, pinned host outputs out, one kernel launch;
+    the bits are those of the device-resident forward, and refilling the bound input buffer is all a new step needs."""
+    from any4_b200.modules import Any4Linear
+
+    gen = torch.Generator().manual_seed(9)
+    lin = Any4Linear(1024, 256, bias=False, device=cuda_device, dtype=torch.bfloat16, group_size=128)
+    _fill_any4(lin, gen)
+    lin.reshape_weight(4)
+    for m in (1, 3):
+        xh = torch.randn(m, 1024, generator=gen).bfloat16().pin_memory()
+        launch, yh = lin.bind_host(xh)
+        for _ in range(3):
+            xh.copy_(torch.randn(m, 1024, generator=gen).bfloat16())
+            launch()
+            torch.cuda.synchronize()
+            assert torch.equal(yh.to(cuda_device), lin(xh.to(cuda_device)))
+    y2 = lin.forward_host(xh)
+    torch.cuda.synchronize()
+    assert torch.equal(y2.to(cuda_device), lin(xh.to(cuda_device)))
+    with pytest.raises(RuntimeError):
+        lin.bind_host(torch.randn(1, 1024).bfloat16())           # not pinned
+    with pytest.raises(RuntimeError):
+        lin.bind_host(xh, out=torch.empty(1, 8).bfloat16().pin_memory())
