@@ -162,9 +162,11 @@ int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_z
     if (rc != TG_OK) return rc;
   }
   if (side == TG_WEIGHT_B) {
-    if (use_mma_sync_b(rows_x, w_rows, k))
-      return launch_gemm_w4_rm_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
-                                 (cudaStream_t)stream);
+    if (use_mma_sync_b(rows_x, w_rows, k)) {
+      rc = launch_gemm_w4_rm_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
+                               (cudaStream_t)stream);
+      if (rc != TG_ERR_UNSUPPORTED) return rc;  // (k beyond that kernel's staging areas: the tcgen05 kernel takes any k)
+    }
     return launch_gemm_w4_tc_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
                                (cudaStream_t)stream);
   }

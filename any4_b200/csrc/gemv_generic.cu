@@ -528,6 +528,30 @@ int launch_gemm_w8_rm(void* y, const void* x, const int32_t* w, const void* sz, 
   return dispatch<W8>(p, side, dt, st);
 }
 
+// 4-bit weights in the A layout through the simple per-k-tile kernel: the fallback of gemv_w4_a.cu for shapes its
+// staging areas cannot hold (very long k at small group sizes); any k, up to 8 activation rows per pass
+int launch_gemm_w4_rm_A_generic(void* y, const void* x, const int32_t* w, const void* sz, const void* lut, const uint8_t* exps,
+                                int lut_stride, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik, bool mx4,
+                                tg_dtype dt, cudaStream_t st) {
+  GParams p{};
+  p.w = reinterpret_cast<const uint32_t*>(w);
+  p.x = (const uint16_t*)x;
+  p.y = (uint16_t*)y;
+  p.sz = (const uint16_t*)sz;
+  p.lut = (const uint16_t*)lut;
+  p.exps = exps;
+  p.lut_stride = lut_stride;
+  p.is_mx4 = mx4 ? 1 : 0;
+  p.rows_x = (int)rows_x;
+  p.w_rows = (int)w_rows;
+  p.k = (int)k;
+  p.k_tiles = (int)div_up(k, 16);
+  p.ik = ik;
+  p.outer_k = (int)div_up(p.k_tiles, ik);
+  p.glog2 = glog2_of(group);
+  return dt == TG_BF16 ? launch_simple<TG_BF16, W4, true>(p, st) : launch_simple<TG_FP16, W4, true>(p, st);
+}
+
 int launch_gemm_w16_rm(void* y, const void* x, const void* w, int64_t rows_x, int64_t w_rows, int64_t k, int ik,
                        tg_weight_side side, tg_dtype dt, cudaStream_t st) {
   GParams p{};

@@ -473,6 +473,10 @@ int launch_a(const Params& p0, int row_blocks, int64_t rows_x, const uint16_t* x
 
 }  // namespace
 
+int launch_gemm_w4_rm_A_generic(void* y, const void* x, const int32_t* w, const void* sz, const void* lut, const uint8_t* exps,
+                                int lut_stride, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik, bool mx4,
+                                tg_dtype dt, cudaStream_t st);  // gemv_generic.cu
+
 int launch_gemm_w4_rm_A(void* y, const void* x, const int32_t* w, const void* sz, const void* lut,
                         const uint8_t* exps, int64_t rows_x, int64_t w_rows, int64_t k, int group, int ik,
                         tg_w4_format fmt, tg_dtype dt, const uint16_t* const_lut, cudaStream_t st) {
@@ -503,10 +507,9 @@ int launch_gemm_w4_rm_A(void* y, const void* x, const int32_t* w, const void* sz
     return cps * 256 <= kMaxXBytes && groups * 128 <= (int64_t)kSzBytes;
   };
   while (splits < 8 && !fits(splits)) ++splits;
-  if (!fits(splits)) {
-    set_error("k = %lld with group %d exceeds what one cluster can stage", (long long)k, group);
-    return TG_ERR_UNSUPPORTED;
-  }
+  if (!fits(splits))  // k too long for the staging areas of one cluster: the simple per-k-tile kernel takes any k
+    return launch_gemm_w4_rm_A_generic(y, x, w, sz, p.lut, exps, p.lut_stride, rows_x, w_rows, k, group, ik, fmt == TG_W4_MX4, dt,
+                                       st);
   p.splits = splits;
   p.chunks_per_split = (int)div_up(chunks, splits);
   p.x_row_bytes = p.chunks_per_split * 256;

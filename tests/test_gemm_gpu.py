@@ -175,6 +175,39 @@ def test_large_shape_linearity_and_rows(cuda_device):
     assert (y0 == 0).all()
 
 
+@pytest.mark.parametrize("fmt,g", [("any4r", 32), ("mx4", 32), ("any4r", 64)])
+def test_mma_sync_kernel_k_forced_split_with_many_row_blocks(fmt, g):
+    """k beyond the mma.sync kernel's staging area forces a cluster split-k WITH more row blocks than
+    clusters fit (n = 4096, k = 8192, group 32 / 64: 128 row blocks, splits >= 2).  Force that kernel
+    (TG_OPT_W4_KERNEL = 2) and compare with the tcgen05 kernel, which is pinned to the reference at this size."""
+    import tinygemm  # noqa: F401
+    from any4_b200 import _native
+
+    ops, lib = torch.ops.tinygemm, _native.capi()
+    dev = torch.device("cuda:0")
+    n, k = 4096, 8192
+    gen = torch.Generator(device=dev).manual_seed(g)
+    x = torch.randn(2, k, device=dev, generator=gen).bfloat16()
+    w = torch.randint(-2**31, 2**31 - 1, (n // 8, k // 64, 32, 2), generator=gen, device=dev, dtype=torch.int64).to(torch.int32)
+    if fmt == "mx4":
+        exps = torch.randint(120, 130, (n, k // 32), generator=gen, device=dev, dtype=torch.int32).to(torch.uint8)
+        run = lambda: ops.tinygemm_y_f16RM_x_f16RM_w_mx4TC(x, w, 32, exps, True)
+    else:
+        lut = (torch.rand(n, 16, device=dev, generator=gen) * 15).sort(1).values.bfloat16() - 8
+        sz = torch.stack([torch.rand(k // g, n, generator=gen, device=dev) * 0.01 + 0.001,
+                          torch.randn(k // g, n, generator=gen, device=dev) * 0.01], 2).bfloat16().contiguous()
+        run = lambda: ops.tinygemm_y_f16RM_x_f16RM_w_any4TC(x, w, g, sz, lut, True)
+    try:
+        assert lib.tg_set_option(2, 1) == 0
+        ref = run()
+        assert lib.tg_set_option(2, 2) == 0
+        got = run()
+    finally:
+        lib.tg_set_option(2, 0)
+    assert ((got.float() - ref.float()).abs() <= 2.0 ** -7 * ref.float().abs() + 2.0 ** -9 * ref.float().abs().max()).all()
+    assert (got == ref).float().mean() > 0.97
+
+
 @pytest.mark.parametrize("fmt", ["any4r", "int4", "mx4"])
 @pytest.mark.parametrize("m", [1, 3, 4])
 def test_tcgen05_kernel_agrees_with_mma_sync_kernel(fmt, m):
@@ -268,3 +301,23 @@ def test_reference_general_mul_case_against_fp32(api):
         exact = (w.float() @ x.float().t()).t().bfloat16()  # the fp32 product, rounded once (weights 0 / 1 dequantise exactly)
         avg_err = float((exact.float() - y[:, :m].float()).abs().sum() / (m * n))
         assert avg_err < 1e-2, (api, m, n, k, avg_err)
+
+
+@pytest.mark.parametrize("side", ["left", "right"])
+def test_very_long_k_small_group(side):
+    """k = 36864 at group 32 is more than the lane-per-row kernels can stage per cluster (32768); the
+    reference accepts it.  Left: falls back to the per-k-tile kernel; right: the tcgen05 kernel takes any k."""
+    import tinygemm_lib.functional as TF
+    from tinygemm_lib.utils import group_quantize_tensor
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(17)
+    n, k, g, m = 32, 36864, 32, 2
+    w = (torch.randn(n, k, generator=gen) * 0.1).bfloat16()
+    x = torch.randn(m, k, generator=gen).bfloat16()
+    codes, sz = group_quantize_tensor(w, n_bit=4, q_group_size=g)
+    wd = dequant.dequant_int4(codes, sz, g, torch.bfloat16)
+    want = dequant.gemm(x, wd)
+    fn = TF.linear_y_f16RM_W_int4TC_x_f16RM if side == "left" else TF.linear_y_f16RM_x_f16RM_W_int4TC
+    y = fn(x.to(dev), codes.to(dev), sz.to(dev), g, 4)
+    assert _tol.frob_rel(y[:, :n].cpu(), want) <= _tol.FROB_REL

@@ -55,6 +55,12 @@ def _worker(rank, world, port, q):
         ok &= close(first, want)
         for _ in range(3):  # walks the ring of workspace buffers: same launch, same bits
             ok &= torch.equal(fused(x), first)   # (never short-circuit a call every rank must make)
+        # several sharded calls before the first output is consumed (q, k, v of one layer) - the ring of
+        # SLOTS output buffers keeps each result valid for SLOTS - 1 further calls
+        held = [fused(x) for _ in range(3)]
+        torch.cuda.synchronize()
+        for hd in held:
+            ok &= torch.equal(hd, first)
         # CUDA-graph replays re-issue the captured exchange (same tag, same buffers) on NEW activations: every replay
         # must deliver this replay's shards, never the previous one's
         torch.cuda.synchronize()
