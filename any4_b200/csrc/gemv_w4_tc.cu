@@ -85,6 +85,8 @@ struct ParamsTC {
   const uint32_t* sz;    // [k/g][w_rows] (scale, zero) pairs (unused for mx4)
   const uint8_t* exps;   // [w_rows][k/g] e8m0, mx4 only
   const uint16_t* lut;   // [16] or [w_rows][16]
+  const uint8_t* xperm;  // MB >= 8: the activations pre-permuted into the operand layout, one kXStageBytes block per stage of
+                         // the row (x_permute_kernel); the TMA producer brings each stage's block in.  null: register path
   unsigned long long* ws_partial;  // this launch's workspace pool
   uint32_t ws_tag;                  // launch tag carried by every partial of this launch
   int64_t tile_stride;   // bytes between consecutive n-tiles of the packed weight = 4 * k
@@ -160,7 +162,7 @@ __device__ __forceinline__ uint32_t tile_off(int t) {
 __device__ __forceinline__ uint32_t odd_hl(int hl) { return (uint32_t)hl * 256u + 128u; }
 // mbarrier i (8 bytes each, 16 per half-line)
 __device__ __forceinline__ uint32_t bar_off(int i) { return odd_hl(kCtrlHl + (i >> 4)) + (uint32_t)(i & 15) * 8u; }
-enum : int { B_WFULL = 0, B_WEMPTY = 3, B_AFULL = 6, B_AEMPTY = 9, B_DFULL = 12, B_DEMPTY = 14, B_COUNT = 16 };
+enum : int { B_WFULL = 0, B_WEMPTY = 3, B_AFULL = 6, B_AEMPTY = 9, B_DFULL = 12, B_DEMPTY = 14, B_XEMPTY = 16, B_XFULL = 19, B_COUNT = 22 };
 constexpr uint32_t kHolderOff = 242u * 256u + 128u;  // TMEM base address; +4: "this CTA is the last arriver" flag
 
 template <int MB, bool XRES>
@@ -225,6 +227,12 @@ __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
   return pred;
+}
+// bulk copy of data that other CTAs read too (the permuted activations): default L2 policy
+__device__ __forceinline__ void bulk_g2s_plain(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // pair-table lookup: the dynamic shared window of a kernel without static shared memory starts at kSmemBase (checked
@@ -344,6 +352,21 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
   pc.init(u_begin, S);
   uint32_t pseq = 0;
   uint64_t pol = 0;
+  // MB >= 8 with pre-permuted activations: a stage's operand block travels with the stage's weights (same barrier)
+  // The activation blocks have their own ring barriers: a weight stage is refilled as soon as the dequant warps have
+  // read it, an activation block only once the stage's MMAs are done.
+  const bool x_tma = MB >= 8 && p.xperm != nullptr;
+  Cursor xpc;  // activation producer cursor
+  xpc.init(u_begin, S);
+  uint32_t xseq = 0;
+  auto produce_x = [&]() {  // lane 0
+    const int s = (int)(xseq % C::NX);
+    const uint32_t bar = sbase + bar_off(B_XFULL + s);
+    mbar_expect_tx(bar, C::kXStageBytes);
+    bulk_g2s_plain(x0 + (uint32_t)s * C::kXStageBytes, p.xperm + (size_t)xpc.sir * C::kXStageBytes, C::kXStageBytes, bar);
+    ++xseq;
+    xpc.next(S);
+  };
   // one ring stage: lane 0 arms the barrier, lanes 0..3 issue one 4 KiB n-tile copy each
   auto produce = [&]() {
     const int s = (int)(pseq % kWStages);
@@ -391,6 +414,8 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
         mbar_init(sbase + bar_off(B_WEMPTY + i), kDqWarps);
         mbar_init(sbase + bar_off(B_AFULL + i), 4);
         mbar_init(sbase + bar_off(B_AEMPTY + i), 1);
+        mbar_init(sbase + bar_off(B_XEMPTY + i), 1);
+        mbar_init(sbase + bar_off(B_XFULL + i), 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(sbase + bar_off(B_DFULL + i), 1);
@@ -642,30 +667,52 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
         const int me = (int)blockIdx.x;
         const int i_first = cta_of_unit(p, rb * S);
         const int i_last = cta_of_unit(p, rb * S + S - 1);
-        for (int idx = (int)threadIdx.x; idx < 32 * p.m; idx += kDqThreads) {
-          float total = block_sum(idx >> 5, idx & 31);
-          if (me != i_first) {
-            const int slot = rb == rb_first ? 0 : 1;
-            const unsigned long long word = ((unsigned long long)p.ws_tag << 32) | (unsigned long long)__float_as_uint(total);
+        constexpr int PER = (32 * MB + kDqThreads - 1) / kDqThreads;  // outputs per thread (2 at 16 rows)
+        float tot[PER];
+        bool act[PER];
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+          const int idx = (int)threadIdx.x + e * kDqThreads;
+          act[e] = idx < 32 * p.m;
+          tot[e] = act[e] ? block_sum(idx >> 5, idx & 31) : 0.f;
+        }
+        if (me != i_first) {
+          const int slot = rb == rb_first ? 0 : 1;
+#pragma unroll
+          for (int e = 0; e < PER; ++e) {
+            if (!act[e]) continue;
+            const int idx = (int)threadIdx.x + e * kDqThreads;
+            const unsigned long long word = ((unsigned long long)p.ws_tag << 32) | (unsigned long long)__float_as_uint(tot[e]);
             asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p.ws_partial + ((size_t)(me * 2 + slot) * 16) * 32 + idx), "l"(word)
                          : "memory");
-          } else {
-            for (int ii = i_first + 1; ii <= i_last; ++ii) {
-              int b0, e0;
-              cta_range(p, ii, b0, e0);
-              const int sl = (b0 / S == rb) ? 0 : 1;
-              unsigned long long* src = p.ws_partial + ((size_t)(ii * 2 + sl) * 16) * 32 + idx;
-              unsigned long long word;
-              do {
-                asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(word) : "l"(src) : "memory");
-              } while ((uint32_t)(word >> 32) != p.ws_tag);
+          }
+        } else {
+          for (int ii = i_first + 1; ii <= i_last; ++ii) {
+            int b0, e0;
+            cta_range(p, ii, b0, e0);
+            const int sl = (b0 / S == rb) ? 0 : 1;
+            unsigned long long* src = p.ws_partial + ((size_t)(ii * 2 + sl) * 16) * 32 + threadIdx.x;
+            // all of this thread's loads first (each one queues behind the weight stream: ~2 us), then the stragglers
+            unsigned long long word[PER];
+#pragma unroll
+            for (int e = 0; e < PER; ++e)
+              if (act[e]) asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(word[e]) : "l"(src + e * kDqThreads) : "memory");
+#pragma unroll
+            for (int e = 0; e < PER; ++e) {
+              if (!act[e]) continue;
+              while ((uint32_t)(word[e] >> 32) != p.ws_tag)
+                asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(word[e]) : "l"(src + e * kDqThreads) : "memory");
               // consumed: clear the word.  A CUDA-graph replay re-launches this kernel with the SAME tag; without the
               // clear its owner could take this launch's partial for its own.  (The next writer of this word is a
               // launch that starts its stores only after this one has completed.)
-              asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(src), "l"(0ull) : "memory");
-              total += __uint_as_float((uint32_t)word);
+              asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(src + e * kDqThreads), "l"(0ull) : "memory");
+              tot[e] += __uint_as_float((uint32_t)word[e]);
             }
-            emit(idx >> 5, idx & 31, total);
+          }
+#pragma unroll
+          for (int e = 0; e < PER; ++e) {
+            const int idx = (int)threadIdx.x + e * kDqThreads;
+            if (act[e]) emit(idx >> 5, idx & 31, tot[e]);
           }
         }
       }
@@ -698,7 +745,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       bar_sync(1, kDqThreads);  // table complete, LUT staging area free again
       if (cur.u + seg_n < u_end) request_lut(rb + 1);
       if constexpr (!XRES) {
-        if (first_seg) {
+        if (first_seg && !x_tma) {
           // the activations are the previous kernel's output: everything up to here overlapped its tail
           if (static_w) griddep_wait();
           x_fill_any();
@@ -814,7 +861,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
             tmem_st8(acol + (uint32_t)(T * 8), r);
           }
         }
-        x_step_any();  // (streamed activations) stage + 1's pieces: their ring slot is free, see the kernel comment
+        if (!x_tma) x_step_any();  // (streamed activations) stage + 1's pieces: their ring slot is free, see the kernel comment
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
@@ -873,10 +920,34 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
     }
   } else if (warp == kDqWarps) {
     // =============================================================== TMA producer: the rest of the stream
-    while (pc.u < u_end) {
-      const int s = (int)(pseq % kWStages);
-      mbar_wait(sbase + bar_off(B_WEMPTY + s), ((pseq / kWStages) - 1u) & 1u);
-      produce();
+    if (x_tma) {
+      // the permuted activations are the previous kernel's output (x_permute_kernel); the weights were not - the copies
+      // of the first stages are long under way
+      if (static_w) griddep_wait();
+      // weights and activations advance independently: whichever ring has a free slot is refilled
+      while (pc.u < u_end || xpc.u < u_end) {
+        auto probe = [&](uint32_t bar, uint32_t parity) {  // lane 0 probes for the warp
+          return __shfl_sync(0xffffffffu, lane == 0 ? mbar_try(bar, parity) : 0u, 0) != 0u;
+        };
+        if (pc.u < u_end) {
+          const int s = (int)(pseq % kWStages);
+          if (pseq < (uint32_t)kWStages || probe(sbase + bar_off(B_WEMPTY + s), ((pseq / kWStages) - 1u) & 1u)) produce();
+        }
+        if (xpc.u < u_end) {
+          const int s = (int)(xseq % C::NX);
+          if (xseq < (uint32_t)C::NX || probe(sbase + bar_off(B_XEMPTY + s), ((xseq / C::NX) - 1u) & 1u)) {
+            if (lane == 0) produce_x();
+            else ++xseq, xpc.next(S);
+            __syncwarp();
+          }
+        }
+      }
+    } else {
+      while (pc.u < u_end) {
+        const int s = (int)(pseq % kWStages);
+        mbar_wait(sbase + bar_off(B_WEMPTY + s), ((pseq / kWStages) - 1u) & 1u);
+        produce();
+      }
     }
   } else {
     // =============================================================== MMA issuer (one warp, one elected lane)
@@ -918,7 +989,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       if (lane == 0) TC_TRACE(50);
       if (static_w) griddep_wait();  // the activations are the previous kernel's output
       if (lane == 0) TC_TRACE(51);
-    } else {
+    } else if (!x_tma) {
       bar_sync(2, kDqThreads + 32);  // the first activations are staged (by the dequant warps)
     }
     Cursor cur;
@@ -952,6 +1023,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
             x_staged |= 1u << t;
           }
         }
+        if (x_tma) mbar_wait(sbase + bar_off(B_XFULL) + (gst % C::NX) * 8u, (gst / C::NX) & 1u);  // the stage's activation block
 #pragma unroll
         for (int Q = 0; Q < 2; ++Q) {
           const uint32_t use = 2u * gst + (uint32_t)Q;
@@ -973,6 +1045,7 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
               acc = 1u;
             }
             tc_commit(sbase + bar_off(B_AEMPTY + slot));
+            if (Q == 1 && x_tma) tc_commit(sbase + bar_off(B_XEMPTY) + (gst % C::NX) * 8u);  // the stage's activation block is free
             if (Q == 1 && i == seg_n - 1) tc_commit(sbase + bar_off(B_DFULL + buf));  // the row block's sums are complete
           }
           acc = 1u;
@@ -1016,16 +1089,55 @@ __global__ void __launch_bounds__(Cfg<MB, XRES>::kThreads, Cfg<MB, XRES>::kMinBl
 }
 
 // ---------------------------------------------------------------------------------------
+// MB >= 8: the activations, permuted ONCE into the operand layout the MMA descriptor describes (instead of by every CTA
+// for every stage through registers: 32 KB per stage at 16 rows, twice the stage's weight bytes).  Block t of the
+// output = the operand block of stage t of a row (kXStageBytes): 16-byte unit (s, h, n) at
+// ((s*2 + h) * G8 + n/8) * 128 + (n%8) * 16 holds K indices 8h..8h+7 of K step s = Q*8 + T for operand row n = 4*mi + j,
+// K index 2c + f <-> k = 1024 t + 128 (4Q + j) + 16 T + c + 8 f; zeros beyond k and beyond the m valid rows.
+// One CTA per stage; PDL citizen like the GEMV that follows it.
+// ---------------------------------------------------------------------------------------
+template <int MB>
+__global__ void __launch_bounds__(256) x_permute_kernel(const uint16_t* __restrict__ x, uint4* __restrict__ out, int m, int k) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  constexpr int G8 = MB / 2;
+  constexpr int kUnits = 16 * 2 * 4 * MB;  // per stage
+  const int t = (int)blockIdx.x;
+  for (int u = (int)threadIdx.x; u < kUnits; u += 256) {
+    const int n = (u & 7) + 8 * ((u >> 3) % G8);
+    const int sh = u / (8 * G8), h = sh & 1, sstep = sh >> 1;
+    const int mi = n >> 2, j = n & 3, Q = sstep >> 3, T = sstep & 7;
+    const int kb = t * 1024 + (Q * 4 + j) * 128 + T * 16 + 4 * h;  // c = 4h .. 4h+3; f = 0: +0, f = 1: +8
+    uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
+    if (mi < m) {
+      const uint16_t* row = x + (int64_t)mi * k;
+      if (kb + 4 <= k) lo = *reinterpret_cast<const uint2*>(row + kb);
+      if (kb + 12 <= k) hi = *reinterpret_cast<const uint2*>(row + kb + 8);
+    }
+    // K indices 8h + i, i = 0..7: (c, f) = (4h + i/2, i & 1) -> lo0 hi0 lo1 hi1 lo2 hi2 lo3 hi3
+    uint4 v;
+    v.x = prmt(lo.x, hi.x, 0x5410u), v.y = prmt(lo.x, hi.x, 0x7632u);
+    v.z = prmt(lo.y, hi.y, 0x5410u), v.w = prmt(lo.y, hi.y, 0x7632u);
+    out[(size_t)t * kUnits + u] = v;
+  }
+}
+constexpr size_t kXPermPoolBytes = 1u << 20;  // 16 rows x 32768 k x 2 bytes
+__device__ __align__(128) uint8_t g_xperm[kWsPools][kXPermPoolBytes];
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 std::atomic<unsigned> g_launch_seq{0};  // launch tag of the split fix-up (one counter for ALL instantiations)
 int g_ctas_per_sm = 0;  // 0 = heuristic (tuning: env TG_TC_CTAS)
 int g_split = -1;       // -1 = heuristic, 0 = whole row blocks per CTA, 1 = stream-K over stages (tuning: env TG_TC_SPLIT)
+bool g_x_tma = true;    // MB >= 8: activations pre-permuted + TMA-staged (tuning: env TG_TC_XTMA=0 -> register-staged)
 
 struct DeviceInfo {
   int n_sm = 0;
   unsigned long long* ws_partial = nullptr;
+  uint8_t* xperm = nullptr;
 };
+std::atomic<unsigned> g_xperm_seq{0};
 static int device_info(DeviceInfo** out) {
   static thread_local DeviceInfo info[kMaxDevices];
   DeviceInfo& d = info[current_device_slot()];
@@ -1034,7 +1146,8 @@ static int device_info(DeviceInfo** out) {
     cudaGetDevice(&dev);
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    if (cudaGetSymbolAddress((void**)&d.ws_partial, g_ws_partial) != cudaSuccess) {
+    if (cudaGetSymbolAddress((void**)&d.ws_partial, g_ws_partial) != cudaSuccess ||
+        cudaGetSymbolAddress((void**)&d.xperm, g_xperm) != cudaSuccess) {
       set_error("cudaGetSymbolAddress failed: %s", cudaGetErrorString(cudaGetLastError()));
       return TG_ERR_CUDA;
     }
@@ -1043,6 +1156,7 @@ static int device_info(DeviceInfo** out) {
     if (!env_read) {
       if (getenv("TG_TC_CTAS")) g_ctas_per_sm = atoi(getenv("TG_TC_CTAS"));
       if (getenv("TG_TC_SPLIT")) g_split = atoi(getenv("TG_TC_SPLIT"));
+      if (getenv("TG_TC_XTMA")) g_x_tma = atoi(getenv("TG_TC_XTMA")) != 0;
       env_read = true;
     }
   }
@@ -1085,7 +1199,7 @@ int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) 
   if (per_sm > C::kMinBlocks) per_sm = C::kMinBlocks;
   int64_t slots = (int64_t)di->n_sm * per_sm;
   if (slots > kMaxGrid) slots = kMaxGrid;
-  constexpr int64_t kFixup = 1;
+  constexpr int64_t kFixup = MB == 16 ? 3 : MB == 8 ? 2 : 1;  // stages a shared row block costs (32 x m partials through global memory)
   const int64_t g_split_ctas = stages < slots ? stages : slots;
   const int64_t g_whole_ctas = row_blocks < slots ? row_blocks : slots;
   const int64_t t_split = div_up(stages, g_split_ctas) + kFixup;
@@ -1160,8 +1274,39 @@ int launch_m(ParamsTC p, const Peers& peers0, int row_blocks, int64_t rows_x, co
     // faster as one 8-row CTA per SM (measured: profiles/r2/kernel_choice.md)
     else if (p.m <= 4 && ((int64_t)row_blocks * p.stages_per_row >= 148 * 10 || peers0.n > 0))
       rc = launch_one<DT, IK, 4, false, MX4, false>(p, peers, row_blocks, st);
-    else if (p.m <= 8) rc = launch_one<DT, IK, 8, false, MX4, false>(p, peers, row_blocks, st);
-    else rc = launch_one<DT, IK, 16, false, MX4, false>(p, peers, row_blocks, st);
+    else {
+      // 5..16 rows: permute the activations once (a tiny PDL-chained kernel) and let the GEMV's TMA producer bring each
+      // stage's operand block in; k too long for the device-global staging pool: the register-staged path
+      const int mb = p.m <= 8 ? 8 : 16;
+      const size_t need = (size_t)p.stages_per_row * (size_t)(32 * (mb / 2) * 128);
+      p.xperm = nullptr;
+      DeviceInfo* di = nullptr;
+      rc = device_info(&di);  // (also reads the tuning environment on the first call)
+      if (rc != TG_OK) return rc;
+      if (need <= kXPermPoolBytes && g_x_tma) {
+        uint8_t* pool = di->xperm + (size_t)(g_xperm_seq.fetch_add(1u, std::memory_order_relaxed) % kWsPools) * kXPermPoolBytes;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)p.stages_per_row, 1, 1);
+        cfg.blockDim = dim3(256, 1, 1);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = g_pdl ? 1 : 0;
+        cudaError_t e = mb == 8 ? cudaLaunchKernelEx(&cfg, x_permute_kernel<8>, p.x, (uint4*)pool, p.m, p.k)
+                                : cudaLaunchKernelEx(&cfg, x_permute_kernel<16>, p.x, (uint4*)pool, p.m, p.k);
+        if (e != cudaSuccess) {
+          set_error("x_permute_kernel launch failed: %s", cudaGetErrorString(e));
+          (void)cudaGetLastError();
+          return TG_ERR_CUDA;
+        }
+        count_launch();
+        p.xperm = pool;
+      }
+      if (mb == 8) rc = launch_one<DT, IK, 8, false, MX4, false>(p, peers, row_blocks, st);
+      else rc = launch_one<DT, IK, 16, false, MX4, false>(p, peers, row_blocks, st);
+    }
     if (rc != TG_OK) return rc;
   }
   return TG_OK;
