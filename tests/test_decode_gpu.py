@@ -114,9 +114,10 @@ def test_fuse_rows(rows):
         lins.append(lin)
     fused = fuse_rows(lins)
     for m in (1, 3):
-        x = torch.randn(m, k, device=dev).bfloat16()
+        x = torch.randn(m, k, device=dev, generator=torch.Generator(device=dev).manual_seed(m)).bfloat16()
         got, want = fused(x), torch.cat([lin(x) for lin in lins], -1)
-        assert ((got.float() - want.float()).abs() <= 2.0 ** -7 * want.float().abs() + 1e-6).all()
+        # (an output that cancels to ~0 may differ by many of ITS ulps: bound relative to the row's scale as well)
+        assert ((got.float() - want.float()).abs() <= 2.0 ** -7 * want.float().abs() + 2.0 ** -9 * want.float().abs().max()).all()
         assert (got == want).float().mean() > 0.98
 
 
@@ -147,11 +148,11 @@ def test_linear_silu_pairs(m, n, k):
     want = TF.silu(yg) * yu
     plain = fused(x).view(m, n, 2)                                 # the interleaved weight through the plain GEMV
     for a, b in ((plain[..., 0], yg), (plain[..., 1], yu)):        # same weights, possibly another summation order
-        assert ((a.float() - b.float()).abs() <= 2.0 ** -7 * b.float().abs() + 1e-6).all()
+        assert ((a.float() - b.float()).abs() <= 2.0 ** -7 * b.float().abs() + 2.0 ** -9 * b.float().abs().max()).all()
         assert (a == b).float().mean() > 0.98
     got = D.linear_silu_pairs(fused, x)
     assert got.shape == (m, n)
-    assert ((got.float() - want.float()).abs() <= 2.0 ** -6 * want.float().abs() + 1e-6).all()
+    assert ((got.float() - want.float()).abs() <= 2.0 ** -6 * want.float().abs() + 2.0 ** -8 * want.float().abs().max()).all()
     assert (got == want).float().mean() > 0.97
     # the fused epilogue IS the plain GEMV + tg_decode_silu_mul, bit for bit
     for r in range(m):
