@@ -1188,14 +1188,14 @@ int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) 
   int rc = device_info(&di);
   if (rc != TG_OK) return rc;
 
-  // Work split.  One CTA per SM while a CTA's share is small (the second slot of every SM is then free for the next
-  // kernel of the stream, whose prologue overlaps our dequant), two per SM for the long ones (they hide each other's
-  // row-block boundaries).  Stream-K over ring stages when that shortens the longest CTA by more than the fix-up
+  // Work split.  One CTA per SM while a CTA's share is small AND there are no more row blocks than SMs (the second
+  // slot of every SM is then free for the next kernel of the stream, whose prologue overlaps our dequant), two per SM
+  // otherwise (they hide each other's row-block boundaries).  Stream-K over ring stages when that shortens the longest CTA by more than the fix-up
   // of a shared row block costs (~kFixup stages), else whole row blocks per CTA.
   const int S = p.stages_per_row;
   const int64_t stages = (int64_t)row_blocks * S;
   int per_sm = g_ctas_per_sm;
-  if (per_sm <= 0) per_sm = (stages >= (int64_t)di->n_sm * 2 * 5) ? 2 : 1;
+  if (per_sm <= 0) per_sm = (stages >= (int64_t)di->n_sm * 2 * 5 || row_blocks > di->n_sm) ? 2 : 1;  // (6144 x 4096: 8.4 -> 6.7 us)
   if (per_sm > C::kMinBlocks) per_sm = C::kMinBlocks;
   int64_t slots = (int64_t)di->n_sm * per_sm;
   if (slots > kMaxGrid) slots = kMaxGrid;
