@@ -57,7 +57,15 @@ __global__ void __launch_bounds__(kNormThreads, 1)
 add_rmsnorm_kernel(uint16_t* __restrict__ h, const uint16_t* __restrict__ delta, const uint16_t* __restrict__ weight,
                    uint16_t* __restrict__ out, int n, float eps) {
   __shared__ float red[kNormThreads / 32];
-  pdl_prologue();
+  // the norm weights are static: fetched before the dependency resolves (one L2 round trip off the critical path)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  uint4 wreg[kNormMaxPerThread / 8];
+#pragma unroll
+  for (int i = 0; i < kNormMaxPerThread / 8; ++i) {
+    const int vi = (int)threadIdx.x + i * kNormThreads;
+    wreg[i] = vi < (n >> 3) ? reinterpret_cast<const uint4*>(weight)[vi] : make_uint4(0, 0, 0, 0);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   uint32_t hp[kNormMaxPerThread / 2];  // the (updated) residual stream, packed pairs
   float ss = 0.f;
   const int nvec = n >> 3;  // 16-byte vectors
@@ -97,7 +105,7 @@ add_rmsnorm_kernel(uint16_t* __restrict__ h, const uint16_t* __restrict__ delta,
   for (int i = 0; i < kNormMaxPerThread / 8; ++i) {
     const int vi = (int)threadIdx.x + i * kNormThreads;
     if (vi < nvec) {
-      const uint4 wv = reinterpret_cast<const uint4*>(weight)[vi];
+      const uint4 wv = wreg[i];
       const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
       uint32_t o[4];
 #pragma unroll
@@ -156,18 +164,34 @@ template <typename T>
 __global__ void __launch_bounds__(kHeadDim, 1)
 rope_attn_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ cosv, const uint16_t* __restrict__ sinv,
                  uint16_t* __restrict__ kc, uint16_t* __restrict__ vc, uint16_t* __restrict__ out, int n_heads,
-                 int n_kv, int pos, int cache_len, float scale) {
+                 int n_kv, int pos, int cache_len, float scale, int n_pre) {
   __shared__ float q_s[kHeadDim], k_s[kHeadDim], sc[kAttnMaxLen + 1], red[4];
-  pdl_prologue();
+  extern __shared__ __align__(16) uint4 kv_s[];  // [n_pre][16] K rows, then [n_pre][16] V rows of this kv head
   const int h = blockIdx.x, kvh = h / (n_heads / n_kv);
   const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+  // Programmatic dependent launch: the cached positions 0..pos-1 were written by EARLIER tokens, not by the kernel this
+  // one depends on (the q|k|v GEMV) - so the first n_pre cache rows are pulled into shared memory (cp.async, no
+  // registers) while that GEMV is still running; only q, the new k and v wait for it.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  {
+    const uint4* kg = reinterpret_cast<const uint4*>(kc + (size_t)kvh * cache_len * kHeadDim);
+    const uint4* vg = reinterpret_cast<const uint4*>(vc + (size_t)kvh * cache_len * kHeadDim);
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(kv_s);
+    for (int i = d; i < n_pre * 16; i += kHeadDim) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + (uint32_t)i * 16u), "l"(kg + i) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + (uint32_t)(n_pre * 16 + i) * 16u), "l"(vg + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const float rope_c = Cvt<T>::f(cosv[d]), rope_s = Cvt<T>::f(sinv[d]);  // static tables: before the wait as well
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint16_t* qh = qkv + (size_t)h * kHeadDim;
   const uint16_t* kh = qkv + (size_t)n_heads * kHeadDim + (size_t)kvh * kHeadDim;
   const uint16_t* vh = qkv + (size_t)(n_heads + n_kv) * kHeadDim + (size_t)kvh * kHeadDim;
   {
     // rotate_half: y[d] = x[d]*cos[d] - x[d+64]*sin[d] (d < 64), y[d] = x[d]*cos[d] + x[d-64]*sin[d] (d >= 64); the
     // framework evaluates x*cos, rot*sin and the sum as three rounded T operations - mirrored here
-    const float c = Cvt<T>::f(cosv[d]), s = Cvt<T>::f(sinv[d]);
+    const float c = rope_c, s = rope_s;
     const int pd = d < 64 ? d + 64 : d - 64;
     const float sgn = d < 64 ? -1.f : 1.f;
     auto rot = [&](const uint16_t* x) {
@@ -183,6 +207,7 @@ rope_attn_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ 
       vc[((size_t)kvh * cache_len + pos) * kHeadDim + d] = vh[d];
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   // scores: thread = (position slot tid/16, 16-byte segment tid%16): 8 cached positions per pass, the loads of
   // kUnroll passes are in flight together (the cache rows come from L2 / HBM: latency, not bandwidth, is the cost)
@@ -197,7 +222,8 @@ rope_attn_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ 
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const int p = p0 + u * 8 + slot;
-      kv[u] = p < pos ? reinterpret_cast<const uint4*>(kbase + (size_t)p * kHeadDim)[seg] : make_uint4(0, 0, 0, 0);
+      kv[u] = p < n_pre ? kv_s[p * 16 + seg]
+                        : (p < pos ? reinterpret_cast<const uint4*>(kbase + (size_t)p * kHeadDim)[seg] : make_uint4(0, 0, 0, 0));
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -249,7 +275,8 @@ rope_attn_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ 
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const int p = p0 + u * 8 + slot;
-      vv[u] = p < pos ? reinterpret_cast<const uint4*>(vbase + (size_t)p * kHeadDim)[seg] : make_uint4(0, 0, 0, 0);
+      vv[u] = p < n_pre ? kv_s[(n_pre + p) * 16 + seg]
+                        : (p < pos ? reinterpret_cast<const uint4*>(vbase + (size_t)p * kHeadDim)[seg] : make_uint4(0, 0, 0, 0));
       pr[u] = p < pos ? sc[p] : 0.f;
     }
 #pragma unroll
@@ -292,11 +319,11 @@ __global__ void __launch_bounds__(256, 1) stage_host_kernel(const uint4* __restr
 }
 
 template <typename... KArgs, typename... Args>
-int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, const char* what, Args... args) {
+int launch_pdl_smem(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const char* what, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -311,6 +338,10 @@ int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, c
   }
   count_launch();
   return TG_OK;
+}
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, const char* what, Args... args) {
+  return launch_pdl_smem(kern, grid, block, 0, st, what, args...);
 }
 
 }  // namespace
@@ -357,13 +388,28 @@ extern "C" int tg_decode_rope_attention(const void* qkv, const void* cos, const 
              cache_len, kAttnMaxLen);
   TG_REQUIRE(dtype == TG_BF16 || dtype == TG_FP16, "%s: bad dtype", fn);
   auto st = (cudaStream_t)stream;
+  // cache rows prefetched before the dependency resolves: up to 192 positions = 96 KB of shared memory (a CTA of this
+  // size still co-resides with one GEMV CTA)
+  constexpr int kPreMax = 192;
+  const int n_pre = pos < kPreMax ? pos : kPreMax;
+  static thread_local bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(rope_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreMax * 512) != cudaSuccess ||
+        cudaFuncSetAttribute(rope_attn_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreMax * 512) != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute failed: %s", fn, cudaGetErrorString(cudaGetLastError()));
+      return TG_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const size_t smem = (size_t)n_pre * 512;
   if (dtype == TG_BF16)
-    return launch_pdl(rope_attn_kernel<__nv_bfloat16>, dim3(n_heads), dim3(kHeadDim), st, fn, (const uint16_t*)qkv,
-                      (const uint16_t*)cos, (const uint16_t*)sin, (uint16_t*)k_cache, (uint16_t*)v_cache, (uint16_t*)out,
-                      n_heads, n_kv_heads, pos, cache_len, scale);
-  return launch_pdl(rope_attn_kernel<__half>, dim3(n_heads), dim3(kHeadDim), st, fn, (const uint16_t*)qkv,
-                    (const uint16_t*)cos, (const uint16_t*)sin, (uint16_t*)k_cache, (uint16_t*)v_cache, (uint16_t*)out,
-                    n_heads, n_kv_heads, pos, cache_len, scale);
+    return launch_pdl_smem(rope_attn_kernel<__nv_bfloat16>, dim3(n_heads), dim3(kHeadDim), smem, st, fn, (const uint16_t*)qkv,
+                           (const uint16_t*)cos, (const uint16_t*)sin, (uint16_t*)k_cache, (uint16_t*)v_cache,
+                           (uint16_t*)out, n_heads, n_kv_heads, pos, cache_len, scale, n_pre);
+  return launch_pdl_smem(rope_attn_kernel<__half>, dim3(n_heads), dim3(kHeadDim), smem, st, fn, (const uint16_t*)qkv,
+                         (const uint16_t*)cos, (const uint16_t*)sin, (uint16_t*)k_cache, (uint16_t*)v_cache, (uint16_t*)out,
+                         n_heads, n_kv_heads, pos, cache_len, scale, n_pre);
 }
 
 extern "C" int tg_gemm_w4_rm_hostio(void* y_host, const void* x_host, void* x_staging, const int32_t* w,

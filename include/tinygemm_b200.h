@@ -256,7 +256,11 @@ int tg_gemm_w4_rm_silu_pairs(void* y, const void* x, const int32_t* w, const voi
                              int inner_k_tiles, tg_w4_format format, tg_dtype dtype, void* stream);
 /* qkv = [n_heads*128 | n_kv_heads*128 | n_kv_heads*128] (output of a fused q|k|v GEMV): rotary embedding
  * (half-rotation, cos/sin [128]) of q and k, append k, v to the caches [n_kv_heads][cache_len][128] at `pos`,
- * attention of the token over positions 0..pos with GQA, out [n_heads*128].  head_dim must be 128, pos <= 512. */
+ * attention of the token over positions 0..pos with GQA, out [n_heads*128].  head_dim must be 128, pos <= 512.
+ * With TG_OPT_PDL the kernel reads cos / sin and the cache rows of positions < pos BEFORE the previous kernel of the
+ * stream has finished (they were written by earlier tokens; only qkv is that kernel's output): do not launch it
+ * directly behind a kernel that writes those cache rows or the tables.  Likewise tg_decode_add_rmsnorm reads `weight`
+ * before the previous kernel has finished. */
 int tg_decode_rope_attention(const void* qkv, const void* cos, const void* sin, void* k_cache, void* v_cache,
                              void* out, int n_heads, int n_kv_heads, int head_dim, int pos, int cache_len,
                              float scale, tg_dtype dtype, void* stream);
