@@ -22,7 +22,7 @@ CAPI_SYMBOLS = (
     "tg_set_option", "tg_last_error", "tg_version", "tg_launch_count", "tg_reset_launch_count",
     "tg_convert_to_A", "tg_convert_from_A", "tg_convert_to_B", "tg_convert_from_B",
     "tg_convert_to_Aint4", "tg_convert_to_Aint8", "tg_convert_to_Bint4", "tg_convert_to_Bint8",
-    "tg_gemm_w4_rm", "tg_gemm_w4_rm_hostio", "tg_gemm_w4_rm_sharded", "tg_gemm_w4_rm_exchange", "tg_gemm_w8_rm", "tg_gemm_w16_rm",
+    "tg_gemm_w4_rm", "tg_gemm_w4_rm_hostio", "tg_gemm_w4_rm_sharded", "tg_gemm_w4_rm_exchange", "tg_gemm_w4_rm_exchange_silu_pairs", "tg_gemm_w8_rm", "tg_gemm_w16_rm",
     "tg_gemm_tc_workspace_bytes", "tg_gemm_w4_tc", "tg_gemm_w8_tc", "tg_gemm_w16_tc",
     "tg_dequant_int4",
     "tg_quantize_any4_rows",
@@ -66,6 +66,8 @@ def capi():
     if hasattr(lib, "tg_gemm_w4_rm_exchange"):
         u32 = ctypes.c_uint32
         lib.tg_gemm_w4_rm_exchange.argtypes = [vp, vp, i32, u32, i32, i64, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
+        if hasattr(lib, "tg_gemm_w4_rm_exchange_silu_pairs"):
+            lib.tg_gemm_w4_rm_exchange_silu_pairs.argtypes = lib.tg_gemm_w4_rm_exchange.argtypes
     if hasattr(lib, "tg_quantize_any4_rows"):
         lib.tg_quantize_any4_rows.argtypes = [vp, vp, i64, i64, i32, i32, i32, ctypes.c_float, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.tg_gemm_w8_rm.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]

@@ -177,7 +177,7 @@ int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_z
 // shared by the two row-sharded entry points; exchange_tag != 0: y_peers are the ranks' exchange buffers and y_local is
 // this rank's plain output
 static int gemm_w4_rm_sharded_impl(const char* fn, void* y_local, void* const* y_peers, int self_rank, uint32_t exchange_tag,
-                                   int n_peers, int64_t y_row_stride, const void* x, const int32_t* w,
+                                   int silu_pairs, int n_peers, int64_t y_row_stride, const void* x, const int32_t* w,
                                    const void* scales_zeros, const void* lut, const uint8_t* exponents, int64_t rows_x,
                                    int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_w4_format format,
                                    tg_dtype dtype, void* stream) {
@@ -190,8 +190,10 @@ static int gemm_w4_rm_sharded_impl(const char* fn, void* y_local, void* const* y
                "%s: the local output must be 4-byte aligned with an even row stride", fn);
     for (int r = 0; r < n_peers; ++r)
       TG_REQUIRE((reinterpret_cast<uintptr_t>(y_peers[r]) & 7u) == 0, "%s: exchange buffer %d is not 8-byte aligned", fn, r);
-    TG_REQUIRE(y_row_stride >= w_rows * n_peers, "%s: output row stride (%lld) smaller than the full row (%lld)", fn,
-               (long long)y_row_stride, (long long)(w_rows * n_peers));
+    TG_REQUIRE(y_row_stride >= (w_rows * n_peers >> (silu_pairs ? 1 : 0)),
+               "%s: output row stride (%lld) smaller than the full row (%lld)", fn, (long long)y_row_stride,
+               (long long)(w_rows * n_peers >> (silu_pairs ? 1 : 0)));
+    TG_REQUIRE(!silu_pairs || w_rows % 4 == 0, "%s: interleaved (gate, up) shards need w_rows %% 4 == 0", fn);
   } else {
     y_local = y_peers[0];
     TG_REQUIRE(y_row_stride >= w_rows, "%s: output row stride (%lld) smaller than the shard (%lld)", fn,
@@ -221,7 +223,8 @@ static int gemm_w4_rm_sharded_impl(const char* fn, void* y_local, void* const* y
   // the in-kernel exchange lives in the tcgen05 kernel; the mma.sync kernel keeps a plain peer-store variant
   if (exchange || !use_mma_sync_b(rows_x, w_rows, k))
     return launch_gemm_w4_tc_B(y_local, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
-                               clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride, 0, self_rank, exchange_tag);
+                               clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride, silu_pairs, self_rank,
+                               exchange_tag);
   return launch_gemm_w4_rm_B(y_local, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
                              clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride);
 }
@@ -230,7 +233,7 @@ int tg_gemm_w4_rm_sharded(void* const* y_peers, int n_peers, int64_t y_row_strid
                           const void* scales_zeros, const void* lut, const uint8_t* exponents, int64_t rows_x,
                           int64_t w_rows, int64_t k, int group, int inner_k_tiles, tg_w4_format format, tg_dtype dtype,
                           void* stream) {
-  return gemm_w4_rm_sharded_impl("tg_gemm_w4_rm_sharded", nullptr, y_peers, 0, 0u, n_peers, y_row_stride, x, w,
+  return gemm_w4_rm_sharded_impl("tg_gemm_w4_rm_sharded", nullptr, y_peers, 0, 0u, 0, n_peers, y_row_stride, x, w,
                                  scales_zeros, lut, exponents, rows_x, w_rows, k, group, inner_k_tiles, format, dtype, stream);
 }
 
@@ -240,7 +243,17 @@ int tg_gemm_w4_rm_exchange(void* y, void* const* xchg_peers, int self_rank, uint
                            int inner_k_tiles, tg_w4_format format, tg_dtype dtype, void* stream) {
   const char* fn = "tg_gemm_w4_rm_exchange";
   TG_REQUIRE(tag != 0u, "%s: the call tag must not be 0", fn);
-  return gemm_w4_rm_sharded_impl(fn, y, xchg_peers, self_rank, tag, n_peers, y_row_stride, x, w, scales_zeros, lut,
+  return gemm_w4_rm_sharded_impl(fn, y, xchg_peers, self_rank, tag, 0, n_peers, y_row_stride, x, w, scales_zeros, lut,
+                                 exponents, rows_x, w_rows, k, group, inner_k_tiles, format, dtype, stream);
+}
+
+int tg_gemm_w4_rm_exchange_silu_pairs(void* y, void* const* xchg_peers, int self_rank, uint32_t tag, int n_peers,
+                                      int64_t y_row_stride, const void* x, const int32_t* w, const void* scales_zeros,
+                                      const void* lut, const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k,
+                                      int group, int inner_k_tiles, tg_w4_format format, tg_dtype dtype, void* stream) {
+  const char* fn = "tg_gemm_w4_rm_exchange_silu_pairs";
+  TG_REQUIRE(tag != 0u, "%s: the call tag must not be 0", fn);
+  return gemm_w4_rm_sharded_impl(fn, y, xchg_peers, self_rank, tag, 1, n_peers, y_row_stride, x, w, scales_zeros, lut,
                                  exponents, rows_x, w_rows, k, group, inner_k_tiles, format, dtype, stream);
 }
 

@@ -625,6 +625,24 @@ __device__ __forceinline__ void gemv_w4_tc_body(const ParamsTC& p, const Peers& 
       const int rows_valid = min(32, p.w_rows - row0);
       auto emit = [&](int mi, int rr, float total) {
         if constexpr (PEERS) {
+          if (peers.tag != 0u && (p.flags & 16)) {
+            // in-kernel exchange of silu(gate) * up over interleaved (gate, up) rows: rows (rr, rr + 1) make output
+            // (row0 + rr) / 2; outputs of rows rr and rr + 2 travel as one tagged 8-byte word.  peers.n_total / col0
+            // count OUTPUTS here (half the weight rows).
+            const uint32_t mine = f32_to_dt<DT>(total);
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+            const uint32_t act = (uint32_t)silu_mul_dt<DT>((uint16_t)mine, (uint16_t)other);  // valid on even rr
+            const uint32_t act2 = __shfl_xor_sync(0xffffffffu, act, 2);
+            if (!(rr & 3) && rr < rows_valid) {
+              const unsigned long long word = ((unsigned long long)peers.tag << 32) | (unsigned long long)(act | (act2 << 16));
+              const int64_t widx = (int64_t)mi * (peers.n_total >> 1) + ((peers.col0 + ((row0 + rr) >> 1)) >> 1);
+#pragma unroll 1
+              for (int r = 0; r < peers.n; ++r)
+                asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(peers.y[r]) + widx), "l"(word)
+                             : "memory");
+            }
+            return;
+          }
           if (peers.tag != 0u) {  // in-kernel exchange: rows (rr, rr + 1) travel as one tagged 8-byte word to every rank
             const uint32_t mine = f32_to_dt<DT>(total);
             const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
@@ -1336,8 +1354,8 @@ int launch_gemm_w4_tc_B(void* y, const void* x, const int32_t* w, const void* sz
   for (int r = 0; r < n_peers; ++r) peers.y[r] = static_cast<uint16_t*>(y_peers[r]);
   peers.tag = exchange_tag;  // != 0: y_peers are the ranks' exchange buffers, y is the plain local output
   peers.self = self_rank;
-  peers.n_total = (int)(w_rows * n_peers);
-  peers.col0 = (int)(w_rows * self_rank);
+  peers.n_total = (int)(w_rows * n_peers) >> (silu_pairs && exchange_tag ? 1 : 0);  // (outputs, not rows, with the activation)
+  peers.col0 = (int)(w_rows * self_rank) >> (silu_pairs && exchange_tag ? 1 : 0);
   p.w = reinterpret_cast<const uint8_t*>(w);
   p.sz = (fmt == TG_W4_MX4) ? nullptr : reinterpret_cast<const uint32_t*>(sz);
   p.exps = (fmt == TG_W4_MX4) ? exps : nullptr;

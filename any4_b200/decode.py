@@ -96,6 +96,14 @@ def rope_attention(qkv, cos, sin, k_cache, v_cache, pos, n_heads, n_kv_heads, he
 
 
 def linear_silu_pairs(lin, x):
+    from .modules import RowShardedLinear
+
+    if isinstance(lin, RowShardedLinear):  # row-sharded: activation AND exchange inside the GEMV kernel
+        return lin.forward_silu_pairs(x)
+    return _linear_silu_pairs_local(lin, x)
+
+
+def _linear_silu_pairs_local(lin, x):
     """`lin`: a packed Any4Linear (weight-on-the-right kernel, per-row LUT, no bias) whose rows interleave a gate and
     an up projection (row 2j = gate_j, row 2j+1 = up_j, see modules.fuse_rows(..., interleave=True)); returns
     silu(gate(x)) * up(x) [m][out_features / 2] from ONE launch (activation fused into the GEMV epilogue)."""

@@ -544,13 +544,25 @@ class RowShardedLinear(torch.nn.Module):
             full = full + self.bias
         return full.view(*lead, self.out_features)
 
-    def _forward_fused(self, x2d):
+    def forward_silu_pairs(self, input):
+        """For a layer whose weight rows alternate gate / up projections (fuse_rows(..., interleave=True)), sharded with
+        `fused=True`: silu(gate) * up AND the exchange both happen in the GEMV kernel
+        (include/tinygemm_b200.h: tg_gemm_w4_rm_exchange_silu_pairs); returns [..., out_features / 2]."""
+        if not self.fused or self.bias is not None:
+            raise RuntimeError("forward_silu_pairs needs fused=True and no bias")
+        if (self.hi - self.lo) % 4:
+            raise RuntimeError("forward_silu_pairs: the shard must hold whole (gate, up) row pairs in pairs of two")
+        lead = input.shape[:-1]
+        y = self._forward_fused(input.view(-1, input.shape[-1]), silu_pairs=True)
+        return y.reshape(*lead, self.out_features // 2)
+
+    def _forward_fused(self, x2d, silu_pairs=False):
         import ctypes
 
         from . import _native
 
         loc = self.local
-        m, n = x2d.shape[0], self.out_features
+        m, n = x2d.shape[0], self.out_features // (2 if silu_pairs else 1)
         if x2d.device != loc.weight.device:
             raise ValueError("RowShardedLinear: input and weights live on different devices")
         ws = _SymmWorkspace.get(self.group, x2d.device, x2d.dtype, m, self.max_features)
@@ -566,7 +578,8 @@ class RowShardedLinear(torch.nn.Module):
         with torch.cuda.device(x2d.device):
             # the exchange completes INSIDE the kernel (tagged words into every rank's buffer, every CTA collects its
             # slice before it exits): no barrier / collective launch follows, consumers are ordered by stream order
-            rc = lib.tg_gemm_w4_rm_exchange(
+            entry = lib.tg_gemm_w4_rm_exchange_silu_pairs if silu_pairs else lib.tg_gemm_w4_rm_exchange
+            rc = entry(
                 ctypes.c_void_p(out.data_ptr()), peers, self.rank, tag, self.world, ws.n_cap,
                 ctypes.c_void_p(x2d.data_ptr()), ctypes.c_void_p(loc.weight.data_ptr()),
                 ctypes.c_void_p(loc.scales_and_zeros.data_ptr()),

@@ -108,9 +108,11 @@ class FusedBlock(torch.nn.Module):
                                     mk(KV_HEADS * HEAD_DIM, HID, s + 3)]), 2 * INTER)
         self.o = shard(mk(HID, HID, s + 4), 2 * INTER)
         # 1 GPU: gate and up rows interleaved (synthetic packed data: any row order is the same workload) so that
-        # silu(gate) * up happens in the GEMV epilogue; sharded: gate | up blocks + the separate silu*mul kernel
-        self.act_in_epilogue = world == 1
-        self.gate_up = (mk(2 * INTER, HID, s + 5) if self.act_in_epilogue else
+        # silu(gate) * up happens in the GEMV epilogue;
+        # sharded with the in-kernel exchange: the same, the shard keeps whole (gate, up) pairs; NCCL exchange: gate | up
+        # blocks + the separate silu*mul kernel
+        self.act_in_epilogue = world == 1 or _FUSED
+        self.gate_up = (shard(mk(2 * INTER, HID, s + 5), 2 * INTER) if self.act_in_epilogue else
                         shard(fuse_rows([mk(INTER, HID, s + 5), mk(INTER, HID, s + 6)]), 2 * INTER))
         self.down = shard(mk(HID, INTER, s + 7), 2 * INTER)
         self.n1 = torch.ones(HID, device=dev, dtype=torch.bfloat16)
@@ -239,7 +241,7 @@ def run_decode(dev, rank, world, dist, steps=50, warmup=5, ctx=128, layers=LAYER
         "config": {"workload": "Llama-3-8B any4 g=128 single-token decode, batch 1 (BASELINE configs[2]/[4])",
                    "layers": layers, "kv_context": ctx, "launch": "one CUDA graph per token",
                    "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world}, exchange per Linear: {exchange}",
-                   "plumbing": ("q|k|v and gate|up row-fused GEMVs (silu*mul in the gate|up epilogue on 1 GPU) + any4_b200.decode kernels, 7-8 launches / layer"
+                   "plumbing": ("q|k|v and gate|up row-fused GEMVs (silu*mul in the gate|up epilogue) + any4_b200.decode kernels, 7 launches / layer"
                                 if plumbing == "fused" else "stock torch ops, 7 GEMV launches / layer"),
                    "lm_head": "any4 g=128 (row-sharded)" if lm_head_any4 else "bf16 (not quantized, as in the reference)"},
         "bytes_per_token_per_gpu": total,

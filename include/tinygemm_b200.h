@@ -177,6 +177,14 @@ int tg_gemm_w4_rm_exchange(void* y, void* const* xchg_peers, int self_rank, uint
                            const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
                            int inner_k_tiles, tg_w4_format format, tg_dtype dtype, void* stream);
 
+/* tg_gemm_w4_rm_exchange over a shard of ROW-INTERLEAVED (gate, up) weights (as tg_gemm_w4_rm_silu_pairs): the epilogue
+ * applies silu(gate) * up and exchanges the w_rows / 2 activated outputs of the shard; `y` receives the full
+ * [rows_x][n_peers * w_rows / 2] result, the exchange buffers hold [rows_x][n_peers * w_rows / 4] words.  w_rows % 4 == 0. */
+int tg_gemm_w4_rm_exchange_silu_pairs(void* y, void* const* xchg_peers, int self_rank, uint32_t tag, int n_peers,
+                                      int64_t y_row_stride, const void* x, const int32_t* w, const void* scales_zeros,
+                                      const void* lut, const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k,
+                                      int group, int inner_k_tiles, tg_w4_format format, tg_dtype dtype, void* stream);
+
 /* int8.  replaces tinygemm_y_f16RM_x_f16RM_w_int8TC (TinyGemm_int8.cu:215-399, :430-457).
  *   inner_k_tiles B layout: 1, 2, 4;  A layout: 1, 2 */
 int tg_gemm_w8_rm(void* y, const void* x, const int32_t* w, const void* scales_zeros, int64_t rows_x,

@@ -77,6 +77,23 @@ def _worker(rank, world, port, q):
             for o in outs:
                 ok &= torch.equal(o, want_r)
         del g
+    # gate / up rows interleaved, sharded: silu(gate) * up and the exchange in ONE kernel == the single-GPU fused epilogue
+    from any4_b200 import decode as D
+    gen = torch.Generator().manual_seed(77)
+    n2, k2 = 2048, 1024
+    gu = Any4Linear(k2, n2, bias=False, device=dev, dtype=torch.bfloat16, group_size=128)
+    gu.weight.data = torch.randint(0, 16, (n2, k2), generator=gen, dtype=torch.int32).to(dev)
+    gu.lut.data = ((torch.rand(n2, 16, generator=gen) * 15).sort(1).values.bfloat16() - 8).to(dev)
+    gu.scales_and_zeros.data = torch.stack([torch.rand(k2 // 128, n2, generator=gen) * 0.02 + 0.001,
+                                            torch.randn(k2 // 128, n2, generator=gen) * 0.02], 2).bfloat16().to(dev)
+    gu.reshape_weight(4)
+    sh = RowShardedLinear(gu, rank, world, fused=True, max_features=4096)
+    for m in (1, 3):
+        xg = torch.randn(m, k2, generator=gen).bfloat16().to(dev)
+        want_act = D.linear_silu_pairs(gu, xg)
+        got_act = D.linear_silu_pairs(sh, xg)
+        ok &= tuple(got_act.shape) == (m, n2 // 2)
+        ok &= close(got_act, want_act)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
