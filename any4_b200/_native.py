@@ -22,7 +22,7 @@ CAPI_SYMBOLS = (
     "tg_set_option", "tg_last_error", "tg_version", "tg_launch_count", "tg_reset_launch_count",
     "tg_convert_to_A", "tg_convert_from_A", "tg_convert_to_B", "tg_convert_from_B",
     "tg_convert_to_Aint4", "tg_convert_to_Aint8", "tg_convert_to_Bint4", "tg_convert_to_Bint8",
-    "tg_gemm_w4_rm", "tg_gemm_w4_rm_hostio", "tg_gemm_w4_rm_sharded", "tg_gemm_w4_rm_exchange", "tg_gemm_w4_rm_exchange_silu_pairs", "tg_gemm_w8_rm", "tg_gemm_w16_rm",
+    "tg_gemm_w4_rm", "tg_gemm_w4_rm_ws", "tg_gemm_w4_rm_workspace_bytes", "tg_repack_Aint4_to_Bint4", "tg_gemm_w4_rm_hostio", "tg_gemm_w4_rm_sharded", "tg_gemm_w4_rm_exchange", "tg_gemm_w4_rm_exchange_silu_pairs", "tg_gemm_w8_rm", "tg_gemm_w16_rm",
     "tg_gemm_tc_workspace_bytes", "tg_gemm_w4_tc", "tg_gemm_w8_tc", "tg_gemm_w16_tc",
     "tg_dequant_int4",
     "tg_quantize_any4_rows",
@@ -59,6 +59,11 @@ def capi():
     for name in ("tg_convert_to_Aint4", "tg_convert_to_Aint8", "tg_convert_to_Bint4", "tg_convert_to_Bint8"):
         getattr(lib, name).argtypes = [vp, vp, i64, i64, i32, vp]
     lib.tg_gemm_w4_rm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, i32, vp]
+    if hasattr(lib, "tg_repack_Aint4_to_Bint4"):
+        lib.tg_repack_Aint4_to_Bint4.argtypes = [vp, vp, i64, i64, i32, i32, vp]
+        lib.tg_gemm_w4_rm_workspace_bytes.argtypes = [i64, i64, i64, i32]
+        lib.tg_gemm_w4_rm_workspace_bytes.restype = ctypes.c_size_t
+        lib.tg_gemm_w4_rm_ws.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, i32, vp, ctypes.c_size_t, vp]
     if hasattr(lib, "tg_gemm_w4_rm_hostio"):
         lib.tg_gemm_w4_rm_hostio.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, i32, vp]
     if hasattr(lib, "tg_gemm_w4_rm_sharded"):  # (absent only in older builds loaded through ANY4_B200_LIB_DIR)

@@ -174,6 +174,32 @@ int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_z
                              (cudaStream_t)stream);
 }
 
+// Several activation rows against an A-layout weight: the A kernel takes one row per launch, so from kRepackMinRows
+// rows on the weight is repacked into the B layout (mostly into L2) and the one-pass tcgen05 kernel runs on that.
+constexpr int64_t kRepackMinRows = 3;
+size_t tg_gemm_w4_rm_workspace_bytes(int64_t rows_x, int64_t w_rows, int64_t k, tg_weight_side side) {
+  if (side != TG_WEIGHT_A || rows_x < kRepackMinRows || k % 64 != 0 || w_rows % 16 != 0) return 0;
+  return (size_t)w_rows * (size_t)k / 2;
+}
+
+int tg_gemm_w4_rm_ws(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
+                     const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group, int inner_k_tiles,
+                     tg_w4_format format, tg_weight_side side, tg_dtype dtype, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  const size_t need = tg_gemm_w4_rm_workspace_bytes(rows_x, w_rows, k, side);
+  if (need == 0 || workspace == nullptr || workspace_bytes < need)
+    return tg_gemm_w4_rm(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, inner_k_tiles, format, side, dtype,
+                         stream);
+  const char* fn = "tg_gemm_w4_rm_ws";
+  const int ik = inner_k_tiles == 0 ? 4 : inner_k_tiles;
+  TG_REQUIRE(ik == 1 || ik == 2 || ik == 4, "%s: A-layout innerKTiles must be 1, 2 or 4 (got %d)", fn, ik);
+  TG_REQUIRE(w != nullptr && aligned16(workspace), "%s: null weight or misaligned workspace", fn);
+  int rc = tg_repack_Aint4_to_Bint4(w, static_cast<int32_t*>(workspace), w_rows, k, ik, 4, stream);
+  if (rc != TG_OK) return rc;
+  return tg_gemm_w4_rm(y, x, static_cast<const int32_t*>(workspace), scales_zeros, lut, exponents, rows_x, w_rows, k, group, 4,
+                       format, TG_WEIGHT_B, dtype, stream);
+}
+
 // shared by the two row-sharded entry points; exchange_tag != 0: y_peers are the ranks' exchange buffers and y_local is
 // this rank's plain output
 static int gemm_w4_rm_sharded_impl(const char* fn, void* y_local, void* const* y_peers, int self_rank, uint32_t exchange_tag,

@@ -247,6 +247,62 @@ __global__ void __launch_bounds__(kThreads) dequant_int4_kernel(const uint32_t* 
 
 using namespace tg;
 
+// ---------------------------------------------------------------------------------------
+// Packed A int4 layout -> packed B int4 layout of the same matrix (no counterpart in the reference).  The two layouts
+// hold the same nibbles in another order: an A word = one k-tile of the row PAIR (g, g+8),
+//   v0..v7 = (g,k0) (g,k0+1) (g+8,k0) (g+8,k0+1) (g,k0+8) (g,k0+9) (g+8,k0+8) (g+8,k0+9)      (TinyGemmConvertA.cu:248-278)
+// a B word = two k-tiles (2j, 2j+1) of ONE row, v0..v3 = k0, k0+1, k0+8, k0+9 of tile 2j, v4..v7 of tile 2j+1
+// (TinyGemmConvertB.cu:280-303); both pack v7 v5 v3 v1 v6 v4 v2 v0 from the top nibble down.  One thread per B word.
+// Used for several activation rows against an A-layout weight (the A kernel takes one row per launch): repack once,
+// mostly into L2, and run the one-pass tcgen05 kernel of the B layout.
+// ---------------------------------------------------------------------------------------
+__global__ void repack_Aint4_to_Bint4_kernel(const uint32_t* __restrict__ a, uint32_t* __restrict__ b, int64_t n_words,
+                                             int k_tiles, int outer_a, int ik_a, int outer_b, int ik_b) {
+  const int wpl = ik_b >> 1;  // B words per lane
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % wpl);
+    const int t = (int)((i / wpl) & 31);
+    const int64_t blk = i / (wpl * 32);
+    const int ko_b = (int)(blk % outer_b);
+    const int64_t nt = blk / outer_b;
+    const int g = t >> 2, q = t & 3;
+    const int64_t row = nt * 8 + g;
+    const int64_t mt = row >> 4;
+    const int rr = (int)(row & 15), ga = rr & 7, hi = rr >> 3;
+    const int ta = 4 * ga + q;
+    uint32_t word = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int T = (ko_b * wpl + j) * 2 + h;
+      uint32_t w = 0;
+      if (T < k_tiles) w = a[((mt * outer_a + T / ik_a) * 32 + ta) * ik_a + (T % ik_a)];
+      w >>= 4 * hi;  // the low row's nibbles sit at bits 0, 8, 16, 24; the high row's 4 bits above
+      // (k0, k0+1, k0+8, k0+9) = A nibbles at bits (0, 16, 8, 24) -> B nibble positions (0, 16, 4, 20) + 8 h
+      word |= ((w & 0xfu) | (((w >> 16) & 0xfu) << 16) | (((w >> 8) & 0xfu) << 4) | (((w >> 24) & 0xfu) << 20)) << (8 * h);
+    }
+    b[i] = word;
+  }
+}
+
+// the common case ik_a = ik_b = 4, k a multiple of 64: a lane's 16-byte A vector (4 k-tiles of its row pair) becomes the
+// 8-byte B vectors of the SAME lane in the two n-tiles of the m-tile - one 16-byte load, two 8-byte stores, all coalesced
+__global__ void repack_Aint4_to_Bint4_ik4_kernel(const uint4* __restrict__ a, uint2* __restrict__ b, int64_t n_vec, int outer) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 w4 = a[v];
+    const int t = (int)(v & 31);
+    const int64_t blk = v >> 5;
+    const int ko = (int)(blk % outer);
+    const int64_t mt = blk / outer;
+    auto half = [](uint32_t w0, uint32_t w1, int hi) {  // two k-tiles of one row -> one B word
+      auto tile = [](uint32_t w) { return (w & 0xfu) | (((w >> 16) & 0xfu) << 16) | (((w >> 8) & 0xfu) << 4) | (((w >> 24) & 0xfu) << 20); };
+      return tile(w0 >> (4 * hi)) | (tile(w1 >> (4 * hi)) << 8);
+    };
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi)
+      b[((2 * mt + hi) * outer + ko) * 32 + t] = make_uint2(half(w4.x, w4.y, hi), half(w4.z, w4.w, hi));
+  }
+}
+
 extern "C" {
 
 int tg_convert_to_A(const void* in, void* out, int64_t m, int64_t k, void* stream) {
@@ -324,6 +380,28 @@ int tg_convert_to_Bint8(const int32_t* in, int32_t* out, int64_t n, int64_t k, i
   if (nT * kS == 0) return TG_OK;
   to_Bint8_kernel<<<grid_for(nT * kS * 32 * ik), kThreads, 0, (cudaStream_t)stream>>>(in, (uint32_t*)out, n, k, nT, kS, ik);
   TG_CHECK_LAUNCH("tg_convert_to_Bint8");
+  return TG_OK;
+}
+
+int tg_repack_Aint4_to_Bint4(const int32_t* in, int32_t* out, int64_t rows, int64_t k, int ik_a, int ik_b, void* stream) {
+  TG_REQUIRE(in && out && rows > 0 && k > 0, "tg_repack_Aint4_to_Bint4: bad arguments");
+  TG_REQUIRE(rows % 16 == 0, "tg_repack_Aint4_to_Bint4: rows (%lld) must be the padded A-layout row count", (long long)rows);
+  TG_REQUIRE(ik_a == 1 || ik_a == 2 || ik_a == 4, "tg_repack_Aint4_to_Bint4: A innerKTiles must be 1, 2 or 4 (got %d)", ik_a);
+  TG_REQUIRE(ik_b == 2 || ik_b == 4 || ik_b == 8, "tg_repack_Aint4_to_Bint4: B innerKTiles must be 2, 4 or 8 (got %d)", ik_b);
+  TG_REQUIRE(k % (ik_b * 16) == 0, "tg_repack_Aint4_to_Bint4: k (%lld) must be a multiple of %d", (long long)k, ik_b * 16);
+  const int k_tiles = (int)(k / 16);
+  const int outer_a = (int)div_up(k_tiles, ik_a), outer_b = k_tiles / ik_b;
+  const int64_t n_words = (rows / 8) * outer_b * 32 * (ik_b / 2);
+  if (ik_a == 4 && ik_b == 4 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
+    const int64_t n_vec = (rows / 16) * outer_b * 32;
+    repack_Aint4_to_Bint4_ik4_kernel<<<grid_for(n_vec), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint2*)out, n_vec,
+                                                                                            outer_b);
+    TG_CHECK_LAUNCH("tg_repack_Aint4_to_Bint4");
+    return TG_OK;
+  }
+  repack_Aint4_to_Bint4_kernel<<<grid_for(n_words), kThreads, 0, (cudaStream_t)stream>>>(
+      (const uint32_t*)in, (uint32_t*)out, n_words, k_tiles, outer_a, ik_a, outer_b, ik_b);
+  TG_CHECK_LAUNCH("tg_repack_Aint4_to_Bint4");
   return TG_OK;
 }
 

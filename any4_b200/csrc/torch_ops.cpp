@@ -317,10 +317,16 @@ at::Tensor run_rm(const Problem& p, WKind kind, const QuantArgs& q, const char* 
   auto y = at::empty({p.rows_x, p.w_rows}, p.x->options());
   int rc = TG_OK;
   switch (kind) {
-    case WKind::W4:
-      rc = tg_gemm_w4_rm(y.data_ptr(), p.x->data_ptr(), (const int32_t*)p.w->data_ptr(), q.sz, q.lut, q.exps, p.rows_x,
-                         p.w_rows, p.k, (int)q.group, p.w_ik, q.fmt, p.side, p.dt, cur_stream());
+    case WKind::W4: {
+      // (several activation rows against an A-layout weight: scratch for the B-layout repack, from the caching allocator)
+      const size_t ws_bytes = tg_gemm_w4_rm_workspace_bytes(p.rows_x, p.w_rows, p.k, p.side);
+      at::Tensor ws;
+      if (ws_bytes) ws = at::empty({(int64_t)ws_bytes}, p.x->options().dtype(at::kByte));
+      rc = tg_gemm_w4_rm_ws(y.data_ptr(), p.x->data_ptr(), (const int32_t*)p.w->data_ptr(), q.sz, q.lut, q.exps, p.rows_x,
+                            p.w_rows, p.k, (int)q.group, p.w_ik, q.fmt, p.side, p.dt, ws_bytes ? ws.data_ptr() : nullptr,
+                            ws_bytes, cur_stream());
       break;
+    }
     case WKind::W8:
       rc = tg_gemm_w8_rm(y.data_ptr(), p.x->data_ptr(), (const int32_t*)p.w->data_ptr(), q.sz, p.rows_x, p.w_rows, p.k,
                          (int)q.group, p.w_ik, p.side, p.dt, cur_stream());

@@ -421,7 +421,7 @@ def run_ours(args):
         wa = [w.view(n // 16, k // 64, 32, 4) for w, _, _ in ws]       # same bytes viewed as the A int4 layout (ik = 4)
         out["m1"]["int4_g128_A_layout(Int4Linear default)"] = timed(
             lambda: [ops.tinygemm_y_f16RM_x_f16RM_w_int4TC(w, x, G, sz, False) for w, (_, _, sz) in zip(wa, ws)])
-        x16 = torch.randn(16, k, device=dev).bfloat16()  # (the A-layout kernel takes one activation row per launch)
+        x16 = torch.randn(16, k, device=dev).bfloat16()  # (>= 3 rows: the weight is repacked into the B layout per call, then one pass)
         out["m16"]["int4_g128_A_layout(Int4Linear default)"] = timed(
             lambda: [ops.tinygemm_y_f16RM_x_f16RM_w_int4TC(w, x16, G, sz, False) for w, (_, _, sz) in zip(wa, ws)])
         # int8 and 16-bit weights (fragment-order kernel, untuned): 8 weight sets are enough to exceed L2 for 16-bit

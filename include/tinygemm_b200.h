@@ -138,6 +138,20 @@ int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_z
                   const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
                   int inner_k_tiles, tg_w4_format format, tg_weight_side side, tg_dtype dtype, void* stream);
 
+/* tg_gemm_w4_rm with scratch memory.  The A-layout kernel takes ONE activation row per launch; with a workspace of
+ * tg_gemm_w4_rm_workspace_bytes(...) bytes (0 = no use for one) several rows against an A-layout weight are computed by
+ * repacking the weight into the B layout (tg_repack_Aint4_to_Bint4, the same nibbles in another order) and running the
+ * one-pass tcgen05 kernel on it.  Same results as the B-layout op on the B-packed weight.  The workspace may be reused
+ * as soon as the call's work on `stream` has completed.  Any other case: identical to tg_gemm_w4_rm. */
+size_t tg_gemm_w4_rm_workspace_bytes(int64_t rows_x, int64_t w_rows, int64_t k, tg_weight_side side);
+int tg_gemm_w4_rm_ws(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
+                     const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group, int inner_k_tiles,
+                     tg_w4_format format, tg_weight_side side, tg_dtype dtype, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* packed A int4 layout [rows/16][ceil(k/16/ik_a)][32][ik_a] -> packed B int4 layout [rows/8][k/(16 ik_b)][32][ik_b/2] of the
+ * same code matrix (rows = the padded A row count; k % (16 ik_b) == 0) */
+int tg_repack_Aint4_to_Bint4(const int32_t* in, int32_t* out, int64_t rows, int64_t k, int ik_a, int ik_b, void* stream);
+
 /* The same GEMM for a decode step whose activations live in PINNED HOST memory and whose result is wanted there
  * (no counterpart in the reference, whose ops take device tensors): one tiny kernel pulls `x_host` (device-accessible
  * pinned memory, unified addressing) into the device buffer `x_staging` [rows_x][k], the GEMV - ordered behind it by

@@ -52,3 +52,28 @@ def test_dequant_int4_debug_op(cuda_device):
     shifts = [0, 16, 4, 20, 8, 24, 12, 28]
     want = torch.stack([((u >> s) & 0xF).float() - 8 for s in shifts], dim=1)
     assert torch.equal(out, want)
+
+
+@pytest.mark.parametrize("ik_a", [1, 2, 4])
+@pytest.mark.parametrize("ik_b", [2, 4, 8])
+def test_repack_Aint4_to_Bint4(ik_a, ik_b, cuda_device):
+    """tg_repack_Aint4_to_Bint4: the packed A layout of a code matrix -> its packed B layout, bit for bit (both layouts
+    hold the same nibbles; the B layout of the reference's own convert op is the oracle)."""
+    import ctypes
+
+    import tinygemm  # noqa: F401
+    from any4_b200 import _native
+
+    ops, lib = torch.ops.tinygemm, _native.capi()
+    gen = torch.Generator().manual_seed(ik_a * 10 + ik_b)
+    for n, k in ((48, 256), (16, 1024), (80, 512)):
+        codes = torch.randint(0, 16, (n, k), generator=gen, dtype=torch.int32).to(cuda_device)
+        a = ops.convert_matrix_to_m16n8k16_Aint4_layout(codes, ik_a)
+        want = ops.convert_matrix_to_m16n8k16_Bint4_layout(codes, ik_b)
+        rows = a.shape[0] * 16
+        got = torch.empty((rows // 8, k // (16 * ik_b), 32, ik_b // 2), dtype=torch.int32, device=cuda_device)
+        rc = lib.tg_repack_Aint4_to_Bint4(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(got.data_ptr()), rows, k, ik_a, ik_b,
+                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, _native.last_error()
+        assert torch.equal(got[: want.shape[0]], want)
+        assert int(got[want.shape[0]:].abs().sum()) == 0   # rows padded to 16 are zero codes
