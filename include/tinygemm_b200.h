@@ -133,7 +133,11 @@ int tg_convert_to_Bint8(const int32_t* in, int32_t* out, int64_t n, int64_t k, i
  *   lut           [16] (global) or [w_rows][16] dtype (any4 only)
  *   exponents     [w_rows][k/group] uint8 e8m0     (mx4 only; dtype must be TG_BF16)
  *   group         32, 64, 128 or 256
- *   inner_k_tiles B layout: 2, 4, 8;  A layout: 1, 2, 4  */
+ *   inner_k_tiles B layout: 2, 4, 8;  A layout: 1, 2, 4
+ * Concurrency: calls on ONE stream (the normal case, CUDA-graph capture and replay included) are always safe.  The
+ * B-layout tensor-core kernel keeps two kinds of device-global scratch, each rotated over 4 pools per launch - the
+ * tagged partial sums of row blocks shared by several CTAs and, from 5 activation rows on, the permuted activations:
+ * launches that may run CONCURRENTLY on different streams are safe as long as no more than 4 of them are in flight. */
 int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_zeros, const void* lut,
                   const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
                   int inner_k_tiles, tg_w4_format format, tg_weight_side side, tg_dtype dtype, void* stream);
