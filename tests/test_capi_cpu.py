@@ -50,6 +50,23 @@ def test_argument_validation_without_gpu(lib):
     assert w4(rows_x=0) == 0         # empty activation: nothing to launch
     assert lib.tg_set_option(0, 1) == 0 and lib.tg_set_option(1, 0) == 0 and lib.tg_set_option(9, 1) == -1
     assert lib.tg_gemm_tc_workspace_bytes(16, 64, 256) >= 16 * 256 * 2 + 16 * 64 * 2
+    # round-2 entry points
+    assert lib.tg_gemm_w4_rm_workspace_bytes(1, 64, 256, 0) == 0            # one row: the A kernel itself
+    assert lib.tg_gemm_w4_rm_workspace_bytes(8, 64, 256, 0) == 64 * 256 // 2  # several rows, A layout: the B repack
+    assert lib.tg_gemm_w4_rm_workspace_bytes(8, 64, 256, 1) == 0            # B layout: nothing to repack
+    assert lib.tg_repack_Aint4_to_Bint4(one, one, 24, 256, 4, 4, None) == -1  # rows not the padded A row count
+    assert lib.tg_repack_Aint4_to_Bint4(one, one, 32, 96, 4, 4, None) == -1   # k % 64
+    f = ctypes.c_float
+    assert lib.tg_quantize_any4_rows(one, None, 8, 200, 128, 4, 300, f(1e-4), None, None, one, one, one, None, 0, None) == -1
+    assert lib.tg_quantize_any4_rows(one, None, 8, 256, 48, 4, 300, f(1e-4), None, None, one, one, one, None, 0, None) == -1
+    assert lib.tg_quantize_any4_rows(one, None, 12, 256, 128, 4, 300, f(1e-4), None, one, one, one, one, None, 0, None) == -1  # packed: n % 8
+    peers = (ctypes.c_void_p * 2)(256, 512)
+    assert lib.tg_gemm_w4_rm_exchange(one, peers, 0, 0, 2, 128, one, one, one, one, None, 1, 64, 256, 128, 4, 2, 0, None) == -1  # tag 0
+    assert lib.tg_gemm_w4_rm_exchange(one, peers, 5, 1, 2, 128, one, one, one, one, None, 1, 64, 256, 128, 4, 2, 0, None) == -1  # bad rank
+    assert lib.tg_gemm_w4_rm_exchange(one, peers, 0, 1, 2, 64, one, one, one, one, None, 1, 64, 256, 128, 4, 2, 0, None) == -1   # stride < full row
+    assert lib.tg_gemm_w4_rm_exchange_silu_pairs(one, peers, 0, 1, 2, 64, one, one, one, one, None, 1, 72, 256, 128, 4, 2, 0,
+                                                 None) == -1                     # stride 64 < 2 * 72 / 2 outputs
+    assert lib.tg_gemm_w4_rm_hostio(one, one, None, one, one, one, None, 1, 64, 256, 128, 4, 2, 1, 0, None) == -1               # no staging buffer
 
 
 EXPECTED_OPS = [
