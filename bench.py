@@ -164,6 +164,11 @@ def cpu_baseline(seconds=12.0):
     """The reference's CPU path (dense dequant + F.linear) on the host cores, bounded sample."""
     from oracle import cpu_path
 
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
+
     n = k = HEADLINE
     gen = torch.Generator().manual_seed(0)
     assign = torch.randint(0, 16, (n, k), generator=gen, dtype=torch.int32)
@@ -193,6 +198,11 @@ def run_reference(args):
         return
     from oracle import cpu_path
 
+    # all the host threads the box offers - torchrun exports OMP_NUM_THREADS=1 to its workers, which would starve this arm
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     n = k = HEADLINE
     per_step = 2  # bounded sample: 2 forwards per step (ours: `copies` GEMVs per step)
     gen = torch.Generator().manual_seed(0)
