@@ -36,13 +36,14 @@ void set_tc_ctas_per_sm(int v);
 // pass and wins wherever a CTA has more than a handful of ring stages to amortise its prologue; for a decode GEMV so
 // small that every SM gets at most one 32-row block of <= 4096 k (4096 x 4096: 64 KB per SM), the mma.sync kernel's 16
 // consumer warps per CTA finish the block faster than the tcgen05 kernel's 8 dequant warps.
-static bool use_mma_sync_b(int64_t rows_x, int64_t w_rows, int64_t k) {
+static bool use_mma_sync_b(int64_t rows_x, int64_t w_rows, int64_t k, int group) {
   static const int env = getenv("TG_W4_KERNEL") ? atoi(getenv("TG_W4_KERNEL")) : 0;  // tuning override
   const int mode = env ? env : g_w4_kernel;
   if (mode == 1) return false;
   if (rows_x > 4) return false;
   if (mode == 2) return true;
-  return rows_x == 1 && k <= 4096 && div_up(w_rows, 32) <= 148;
+  // (groups of 32 / 64 - mx4, any4 g32: 4 group words per 128 k - are 4-5 % faster on the tcgen05 kernel even there)
+  return rows_x == 1 && k <= 4096 && div_up(w_rows, 32) <= 148 && group >= 128;
 }
 int launch_quantize_any4_rows(const void* w, const float* sample_weight, int64_t n, int64_t k, int group, int inner_k_tiles,
                               int max_iter, float tol, int32_t* codes, int32_t* packed, void* sz, void* any4, void* lut,
@@ -162,7 +163,7 @@ int tg_gemm_w4_rm(void* y, const void* x, const int32_t* w, const void* scales_z
     if (rc != TG_OK) return rc;
   }
   if (side == TG_WEIGHT_B) {
-    if (use_mma_sync_b(rows_x, w_rows, k)) {
+    if (use_mma_sync_b(rows_x, w_rows, k, group)) {
       rc = launch_gemm_w4_rm_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
                                (cudaStream_t)stream);
       if (rc != TG_ERR_UNSUPPORTED) return rc;  // (k beyond that kernel's staging areas: the tcgen05 kernel takes any k)
@@ -247,7 +248,7 @@ static int gemm_w4_rm_sharded_impl(const char* fn, void* y_local, void* const* y
     if (rc != TG_OK) return rc;
   }
   // the in-kernel exchange lives in the tcgen05 kernel; the mma.sync kernel keeps a plain peer-store variant
-  if (exchange || !use_mma_sync_b(rows_x, w_rows, k))
+  if (exchange || !use_mma_sync_b(rows_x, w_rows, k, group))
     return launch_gemm_w4_tc_B(y_local, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype,
                                clut, (cudaStream_t)stream, y_peers, n_peers, y_row_stride, silu_pairs, self_rank,
                                exchange_tag);
@@ -327,7 +328,7 @@ int tg_gemm_w4_rm_silu_pairs(void* y, const void* x, const int32_t* w, const voi
     rc = const_lut_for(format, dtype, (cudaStream_t)stream, &clut);
     if (rc != TG_OK) return rc;
   }
-  if (!use_mma_sync_b(rows_x, w_rows, k))
+  if (!use_mma_sync_b(rows_x, w_rows, k, group))
     return launch_gemm_w4_tc_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
                                (cudaStream_t)stream, nullptr, 0, 0, /*silu_pairs=*/1);
   return launch_gemm_w4_rm_B(y, x, w, scales_zeros, lut, exponents, rows_x, w_rows, k, group, ik, format, dtype, clut,
