@@ -183,6 +183,12 @@ def run_decode(dev, rank, world, dist, steps=50, warmup=5, ctx=128, layers=LAYER
         if os.environ.get("LLAMA_DEBUG"):
             print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
 
+    if lib is not None:
+        # TG_OPT_W4_KERNEL = 1: the tcgen05 kernel for every B-layout 4-bit GEMV.  The automatic choice sends the one
+        # 4096 x 4096 projection to the mma.sync kernel, which wins in a chain of such GEMVs (bench.py's headline) but
+        # needs a whole SM; between the small kernels of a decoder layer the 113 KB tcgen05 CTAs co-reside with their
+        # neighbours and win (533 -> 555 tok/s on 1 GPU).
+        lib.tg_set_option(2, 1)
     with torch.no_grad():
         note("building model")
         global _FUSED
@@ -224,6 +230,8 @@ def run_decode(dev, rank, world, dist, steps=50, warmup=5, ctx=128, layers=LAYER
             ms = float(t.item())
         clocks = sampler.stop() if sampler else None
         del g, out, model  # a live CUDA graph holding NCCL kernels keeps destroy_process_group() from returning
+        if lib is not None:
+            lib.tg_set_option(2, 0)
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
     if rank != 0:
@@ -243,7 +251,8 @@ def run_decode(dev, rank, world, dist, steps=50, warmup=5, ctx=128, layers=LAYER
                    "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world}, exchange per Linear: {exchange}",
                    "plumbing": ("q|k|v and gate|up row-fused GEMVs (silu*mul in the gate|up epilogue) + any4_b200.decode kernels, 7 launches / layer"
                                 if plumbing == "fused" else "stock torch ops, 7 GEMV launches / layer"),
-                   "lm_head": "any4 g=128 (row-sharded)" if lm_head_any4 else "bf16 (not quantized, as in the reference)"},
+                   "lm_head": "any4 g=128 (row-sharded)" if lm_head_any4 else "bf16 (not quantized, as in the reference)",
+                   "options": None if reference else "TG_OPT_STATIC_WEIGHTS = 1, TG_OPT_W4_KERNEL = 1 (tcgen05 kernel for every 4-bit GEMV)"},
         "bytes_per_token_per_gpu": total,
         "roofline": {"bound": "hbm", "achieved": total / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": total / (ms * 1e-3) / 1e9 / peak, "peak_source": src + " (of measured)"},
