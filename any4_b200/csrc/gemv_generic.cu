@@ -11,10 +11,15 @@
 // int8 with bit patterns + one exact HSUB2 + the reference's single-rounded FMA, and feeds the words straight into
 // mma.sync (fp32 accumulation of exact products).  Warps are combined through shared memory, one RN at the end.
 // gemm_frag_kernel: the simple per-k-tile FFMA version, kept for k too long to stage the activations.
+#include <cstdlib>
+
 #include "common.cuh"
-#include "w4_common.cuh"  // mma16816
+#include "w4_common.cuh"  // mma16816, mbarrier / bulk-copy helpers
 
 namespace tg {
+namespace w4 {
+extern bool g_pdl, g_static_weights;  // tg_set_option (gemv_w4_b.cu)
+}
 namespace {
 
 constexpr int kWarps = 8;
@@ -439,6 +444,263 @@ __global__ void __launch_bounds__(kThreads, TG_STREAM_MINB) gemm_stream_kernel(c
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Ring variant for int8 weights and up to 8 activation rows (the decode case; both layouts).
+//  * The weight is always the mma's 16-row A operand and the activations its 8-column B operand: the A layout is that
+//    fragment already; in the B layout a lane's words of two ADJACENT 8-row tiles are exactly (a0, a2) and (a1, a3) of
+//    a 16-row fragment, so a pair of tiles is processed together - one mma and one pair of activation loads per 16
+//    rows x 16 k, no zero operands (the stream kernel spends an mma per 8 rows and zero-fills half its A operand).
+//  * A row tile's packed words are one contiguous run, so a producer warp streams them as bulk-TMA copies (16 KiB per
+//    stage: 1024 k of 16 rows) into a shared-memory ring: bytes in flight do not depend on registers or occupancy, and
+//    the ring keeps filling across row tiles while the consumers reduce.  The (scale, zero) words of those 1024 k
+//    travel in the same stage: the producer fetches them one item ahead into registers and stores them next to the
+//    chunk before it arms the barrier.
+//  * Eight consumer warps take the chunk's units round-robin (conflict-free 16-byte shared loads) and decode a word
+//    (two fragment pairs) with byte permutes instead of shifts and masks.  One block barrier per row tile
+//    (double-buffered partial sums).
+// PDL: dependents are released at entry; the weight stream starts before `griddepcontrol.wait` when the caller
+// declared the weights static (TG_OPT_STATIC_WEIGHTS), the activations are always read after it.
+// ---------------------------------------------------------------------------------------
+constexpr int kRingChunk = 16 * 1024;                            // packed-weight bytes per stage
+constexpr int kRingSzWords = 512;                                // (scale, zero) words per stage (group 32: 32 groups x 16 rows)
+constexpr int kRingStageBytes = kRingChunk + kRingSzWords * 4;
+constexpr int kRingThreads = kThreads + 32;                      // + producer warp
+constexpr int kRingCtrl = 128;                                   // barriers
+constexpr int kRingRedBytes = 2 * kWarps * 4 * 32 * 4;
+constexpr int kRingMaxStages = 4;
+constexpr int kRingMaxX = 144 * 1024;                            // activation area (one CTA per SM beyond ~30 KiB)
+constexpr int ring_fixed_bytes(int stages) { return kRingCtrl + stages * kRingStageBytes + kRingRedBytes; }
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+
+template <int N>
+__device__ __forceinline__ void lds_words(uint32_t addr, uint32_t* dst) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+      const uint4 v = w4::lds128(addr + 16 * i);
+      dst[4 * i] = v.x, dst[4 * i + 1] = v.y, dst[4 * i + 2] = v.z, dst[4 * i + 3] = v.w;
+    }
+  } else if constexpr (N == 2) {
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(dst[0]), "=r"(dst[1]) : "r"(addr));
+  } else {
+    static_assert(N == 1, "1, 2 or a multiple of 4 words");
+    dst[0] = w4::lds32(addr);
+  }
+}
+
+// One packed word = two fragment pairs: bytes (0, 2) -> `lo`, bytes (1, 3) -> `hi`; each value (code - 128) * s + z,
+// single-rounded in the activation dtype (the arithmetic of decode8_pair, with PRMT doing extraction and exponent
+// insertion at once).
+template <tg_dtype DT>
+__device__ __forceinline__ void decode8_word(uint32_t word, uint32_t s_lo, uint32_t z_lo, uint32_t s_hi, uint32_t z_hi,
+                                             uint32_t& lo, uint32_t& hi) {
+  if constexpr (DT == TG_FP16) {
+    const uint32_t h0 = __byte_perm(word, 0x64646464u, 0x4240), h1 = __byte_perm(word, 0x64646464u, 0x4341);  // 1024 + b
+    const __half2 off = __floats2half2_rn(1152.f, 1152.f);
+    const __half2 v0 = __hsub2(*reinterpret_cast<const __half2*>(&h0), off);
+    const __half2 v1 = __hsub2(*reinterpret_cast<const __half2*>(&h1), off);
+    const __half2 r0 = __hfma2(v0, *reinterpret_cast<const __half2*>(&s_lo), *reinterpret_cast<const __half2*>(&z_lo));
+    const __half2 r1 = __hfma2(v1, *reinterpret_cast<const __half2*>(&s_hi), *reinterpret_cast<const __half2*>(&z_hi));
+    lo = *reinterpret_cast<const uint32_t*>(&r0);
+    hi = *reinterpret_cast<const uint32_t*>(&r1);
+  } else {
+    // t = 128 + (b & 127) and offset = 256 - (b & 128) are exact in bf16, and so is t - offset = b - 128
+    const uint32_t m = word & 0x7f7f7f7fu, nh = ~word & 0x80808080u;
+    const uint32_t t0 = __byte_perm(m, 0x43434343u, 0x4240), t1 = __byte_perm(m, 0x43434343u, 0x4341);
+    const uint32_t o0 = __byte_perm(nh, 0x43434343u, 0x4240), o1 = __byte_perm(nh, 0x43434343u, 0x4341);
+    const __nv_bfloat162 v0 = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&t0), *reinterpret_cast<const __nv_bfloat162*>(&o0));
+    const __nv_bfloat162 v1 = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&t1), *reinterpret_cast<const __nv_bfloat162*>(&o1));
+    const __nv_bfloat162 r0 = __hfma2(v0, *reinterpret_cast<const __nv_bfloat162*>(&s_lo), *reinterpret_cast<const __nv_bfloat162*>(&z_lo));
+    const __nv_bfloat162 r1 = __hfma2(v1, *reinterpret_cast<const __nv_bfloat162*>(&s_hi), *reinterpret_cast<const __nv_bfloat162*>(&z_hi));
+    lo = *reinterpret_cast<const uint32_t*>(&r0);
+    hi = *reinterpret_cast<const uint32_t*>(&r1);
+  }
+}
+
+template <tg_dtype DT, bool ALAYOUT, int IK>
+__global__ void __launch_bounds__(kRingThreads, 2) gemm_w8_ring_kernel(const GParams p, int kpad, int static_w, int stages) {
+  constexpr int ROWS = 16;                       // weight rows per item: one A-layout tile, or two adjacent B-layout tiles
+  constexpr int NT = ALAYOUT ? 1 : 2;            // packed tiles per item
+  constexpr int NWT = ALAYOUT ? 2 * IK : IK;     // words per lane per unit of one packed tile
+  constexpr int SUB = kRingChunk / NT;           // bytes of one packed tile per stage
+  constexpr int UC = SUB / (128 * NWT);          // units per chunk (= 64 / IK)
+  constexpr int UPW = UC / kWarps;               // units per warp per chunk
+  constexpr int CK = UC * IK * 16;               // k per chunk
+  static_assert(UPW >= 1 && UPW * NT * NWT == 16 && CK == 1024, "a warp owns 16 words per lane per chunk");
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const uint32_t base = w4::smem_u32(ring_smem);
+  const uint32_t bar_full = base, bar_empty = base + 8 * kRingMaxStages, stage0 = base + kRingCtrl;
+  float* red = reinterpret_cast<float*>(ring_smem + kRingCtrl + stages * kRingStageBytes);      // [2][kWarps][4][32]
+  uint16_t* xs = reinterpret_cast<uint16_t*>(ring_smem + kRingCtrl + stages * kRingStageBytes + kRingRedBytes);  // [rows_x][kpad + 8]
+
+  const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      w4::mbar_init(bar_full + 8 * s, 1);
+      w4::mbar_init(bar_empty + 8 * s, kWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __syncthreads();
+
+  const int n_units = p.outer_k, n_items = p.w_rows / ROWS;
+  const int n_chunks = (n_units + UC - 1) / UC;
+  const int n_groups = p.k >> p.glog2;
+  const int gc = CK >> p.glog2;  // groups per chunk
+  const uint32_t* szw = reinterpret_cast<const uint32_t*>(p.sz);
+
+  if (warp == kWarps) {  // ---- producer ----
+    if (!static_w) asm volatile("griddepcontrol.wait;" ::: "memory");
+    const uint64_t pol = w4::l2_evict_first_policy();
+    const int nj = (gc * ROWS) >> 5;  // group words per lane per chunk: 16 / 8 / 4 / 2 for groups of 32 / 64 / 128 / 256
+    uint32_t szr[16];
+    auto load_sz = [&](int rt, int c) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int i = t + 32 * j;
+        const int grp = c * gc + i / ROWS;
+        szr[j] = (j < nj && grp < n_groups) ? __ldg(szw + (int64_t)grp * p.w_rows + rt * ROWS + (i % ROWS)) : 0u;
+      }
+    };
+    int rt = blockIdx.x, it = 0, s = 0;
+    uint32_t ph = 1;  // first pass over the ring: the slots are free
+    if (rt < n_items) load_sz(rt, 0);
+    for (; rt < n_items; rt += gridDim.x) {
+      for (int c = 0; c < n_chunks; ++c, ++it) {
+        const uint32_t st = stage0 + s * kRingStageBytes;
+        w4::mbar_wait(bar_empty + 8 * s, ph);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nj) w4::sts32(st + kRingChunk + (t + 32 * j) * 4, szr[j]);
+        __syncwarp();
+        if (t == 0) {
+          const int u0 = c * UC;
+          const int nu = min(UC, n_units - u0);
+          const uint32_t bytes = (uint32_t)nu * 128u * NWT;
+          w4::mbar_expect_tx(bar_full + 8 * s, bytes * NT);  // release: the group words above are visible with the chunk
+#pragma unroll
+          for (int h = 0; h < NT; ++h)
+            w4::bulk_g2s(st + h * SUB, p.w + ((int64_t)(rt * NT + h) * n_units + u0) * 32 * NWT, bytes, bar_full + 8 * s, pol);
+        }
+        int nrt = rt, nc = c + 1;
+        if (nc == n_chunks) nc = 0, nrt = rt + (int)gridDim.x;
+        if (nrt < n_items) load_sz(nrt, nc);
+        if (++s == stages) s = 0, ph ^= 1;
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int g = t >> 2, q = t & 3;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  {
+    const bool vec_ok = ((p.k & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+    const int xstride = kpad + 8;  // 4 * odd words: the 8 rows x 4 k-pairs one operand load touches fall into 32 banks
+    for (int i = threadIdx.x; i < p.rows_x * (kpad >> 3); i += kThreads) {
+      const int a = i / (kpad >> 3), c = (i % (kpad >> 3)) * 8;
+      const uint16_t* xr = p.x + (int64_t)a * p.k;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (c + 8 <= p.k && vec_ok) {
+        v = *reinterpret_cast<const uint4*>(xr + c);
+      } else {
+        uint16_t e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = (c + j < p.k) ? xr[c + j] : (uint16_t)0;
+        v = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+      }
+      *reinterpret_cast<uint4*>(xs + (size_t)a * xstride + c) = v;
+    }
+  }
+  consumer_barrier();
+  const int na = p.rows_x;
+  const bool has_x = g < na;  // this lane's activation row (B operand column g)
+  const uint32_t x_lane = w4::smem_u32(xs) + ((has_x ? g : 0) * (kpad + 8) + 2 * q) * 2;
+  const bool one_group_per_unit = (1 << p.glog2) >= IK * 16;
+
+  int s = 0, buf = 0;
+  uint32_t ph = 0;
+  for (int rt = blockIdx.x; rt < n_items; rt += gridDim.x, buf ^= 1) {
+    float acc[2][4];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+
+    for (int c = 0; c < n_chunks; ++c) {
+      const uint32_t st = stage0 + s * kRingStageBytes;
+      const int u0 = c * UC;
+      const int nu = min(UC, n_units - u0);
+      const int gmax = min(gc, n_groups - c * gc) - 1;
+      w4::mbar_wait(bar_full + 8 * s, ph);
+      uint32_t raw[UPW][NT * NWT];
+#pragma unroll
+      for (int j = 0; j < UPW; ++j) {
+        const int ul = warp + j * kWarps;
+        if (ul < nu) {
+#pragma unroll
+          for (int h = 0; h < NT; ++h) lds_words<NWT>(st + h * SUB + (uint32_t)(ul * 32 + t) * NWT * 4, &raw[j][h * NWT]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < UPW; ++j) {
+        const int ul = warp + j * kWarps;
+        if (ul < nu) {
+          uint32_t s2[2], z2[2];
+          auto group_words = [&](int k_local) {
+            const int grp = min(k_local >> p.glog2, gmax);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t v = w4::lds32(st + kRingChunk + (grp * ROWS + g + 8 * h) * 4);
+              s2[h] = __byte_perm(v, 0, 0x1010);
+              z2[h] = __byte_perm(v, 0, 0x3232);
+            }
+          };
+          if (one_group_per_unit) group_words(ul * IK * 16);
+#pragma unroll
+          for (int ki = 0; ki < IK; ++ki) {
+            if (!one_group_per_unit) group_words((ul * IK + ki) * 16);
+            uint32_t a0, a1, a2, a3;
+            if constexpr (ALAYOUT) {  // word 0: (row g, row g + 8) at k 2q..2q+1, word 1: the same rows at k + 8
+              decode8_word<DT>(raw[j][2 * ki], s2[0], z2[0], s2[1], z2[1], a0, a1);
+              decode8_word<DT>(raw[j][2 * ki + 1], s2[0], z2[0], s2[1], z2[1], a2, a3);
+            } else {                  // a word of the first tile: row g at (k, k + 8); of the second: row g + 8
+              decode8_word<DT>(raw[j][ki], s2[0], z2[0], s2[0], z2[0], a0, a2);
+              decode8_word<DT>(raw[j][IK + ki], s2[1], z2[1], s2[1], z2[1], a1, a3);
+            }
+            const uint32_t xa = x_lane + (uint32_t)((u0 + ul) * IK + ki) * 32;
+            const uint32_t x0 = has_x ? w4::lds32(xa) : 0u;
+            const uint32_t x1 = has_x ? w4::lds32(xa + 16) : 0u;
+            w4::mma16816<DT>(acc[(ki + j) & 1], a0, a1, a2, a3, x0, x1);
+          }
+        }
+      }
+      __syncwarp();
+      if (t == 0) mbar_arrive(bar_empty + 8 * s);
+      if (++s == stages) s = 0, ph ^= 1;
+    }
+
+    float* rb = red + buf * (kWarps * 4 * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rb[(warp * 4 + i) * 32 + t] = acc[0][i] + acc[1][i];
+    consumer_barrier();  // (the buffer written two tiles ago was read before the barrier of the previous tile)
+    if (threadIdx.x < 128) {
+      // C fragment: c0, c1 = (weight row g, activation rows 2q, 2q + 1), c2, c3 = (weight row g + 8, ...)
+      const int ci = threadIdx.x >> 5;
+      float sum = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < kWarps; ++w2) sum += rb[(w2 * 4 + ci) * 32 + t];
+      const int wrow = g + 8 * (ci >> 1), act = 2 * q + (ci & 1);
+      if (act < na) p.y[(int64_t)act * p.w_rows + rt * ROWS + wrow] = from_f32<DT>(sum);
+    }
+  }
+}
+
 template <tg_dtype DT, Kind KIND, bool ALAYOUT>
 int launch_simple(const GParams& p, cudaStream_t st) {
   const int tiles = p.w_rows / (ALAYOUT ? 16 : 8);
@@ -487,9 +749,77 @@ int launch_stream(const GParams& p, cudaStream_t st) {
   return launch_stream_a<DT, KIND, ALAYOUT, IK, false>(p, rows_per_pass, kpad, st);
 }
 
+// int8 through the ring kernel, in passes of up to 8 activation rows (the weight of a second pass usually comes from
+// L2): TG_OK / TG_ERR_UNSUPPORTED (use the stream kernel)
+template <tg_dtype DT, bool ALAYOUT, int IK>
+int launch_ring(const GParams& p0, cudaStream_t st) {
+  static const int enabled = [] { const char* e = getenv("TG_W8_RING"); return e ? atoi(e) : 1; }();
+  static const int ctas_env = [] { const char* e = getenv("TG_W8_CTAS"); return e ? atoi(e) : 0; }();
+  const int kpad = p0.outer_k * IK * 16;
+  const size_t row_bytes = (size_t)(kpad + 8) * 2;
+  int per_pass = (int)((size_t)kRingMaxX / row_bytes);
+  if (per_pass > 8) per_pass = 8;
+  if (!enabled || per_pass < 1 || (p0.w_rows & 15) != 0 || (reinterpret_cast<uintptr_t>(p0.w) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(p0.sz) & 3) != 0)
+    return TG_ERR_UNSUPPORTED;
+  auto kern = gemm_w8_ring_kernel<DT, ALAYOUT, IK>;
+  static thread_local int ready[kMaxDevices] = {}, n_sm = 0;
+  int& rdy = ready[current_device_slot()];
+  if (!rdy) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_fixed_bytes(kRingMaxStages) + kRingMaxX) !=
+        cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm_w8_ring_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return TG_ERR_CUDA;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    rdy = 1;
+  }
+  const int items = p0.w_rows / 16;
+  for (int r0 = 0; r0 < p0.rows_x; r0 += per_pass) {
+    GParams p = p0;
+    p.rows_x = p0.rows_x - r0 < per_pass ? p0.rows_x - r0 : per_pass;
+    p.x = p0.x + (int64_t)r0 * p0.k;
+    p.y = p0.y + (int64_t)r0 * p0.w_rows;
+    const size_t xbytes = (size_t)p.rows_x * row_bytes;
+    // two CTAs per SM while four stages + the activations fit 113 KiB, one (with the whole 227 KiB) beyond that
+    const int per_sm = ctas_env > 0 ? ctas_env : (ring_fixed_bytes(kRingMaxStages) + xbytes <= 113 * 1024 ? 2 : 1);
+    const int slots = per_sm * n_sm;  // persistent: the resident CTAs walk over the row tiles
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(items < slots ? items : slots), 1, 1);
+    cfg.blockDim = dim3(kRingThreads, 1, 1);
+    cfg.dynamicSmemBytes = ring_fixed_bytes(kRingMaxStages) + xbytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = w4::g_pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, kpad, (int)(w4::g_static_weights ? 1 : 0), (int)kRingMaxStages);
+    if (e != cudaSuccess) {
+      set_error("gemm_w8_ring_kernel launch failed: %s", cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return TG_ERR_CUDA;
+    }
+    count_launch();
+  }
+  return TG_OK;
+}
+
 template <tg_dtype DT, Kind KIND, bool ALAYOUT>
 int launch(const GParams& p, cudaStream_t st) {
   if (KIND == W16 && ALAYOUT) return launch_stream<DT, KIND, ALAYOUT, 1>(p, st);  // no inner k in this layout
+  if constexpr (KIND == W8) {
+    int rc = TG_ERR_UNSUPPORTED;
+    switch (p.ik) {
+      case 1: rc = launch_ring<DT, ALAYOUT, 1>(p, st); break;
+      case 2: rc = launch_ring<DT, ALAYOUT, 2>(p, st); break;
+      case 4: rc = launch_ring<DT, ALAYOUT, 4>(p, st); break;
+      case 8: rc = launch_ring<DT, ALAYOUT, 8>(p, st); break;
+    }
+    if (rc != TG_ERR_UNSUPPORTED) return rc;
+  }
   switch (p.ik) {
     case 1: return launch_stream<DT, KIND, ALAYOUT, 1>(p, st);
     case 2: return launch_stream<DT, KIND, ALAYOUT, 2>(p, st);
