@@ -540,8 +540,8 @@ __global__ void __launch_bounds__(kRingThreads, 2) gemm_w8_ring_kernel(const GPa
   const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
-      w4::mbar_init(bar_full + 8 * s, 1);
-      w4::mbar_init(bar_empty + 8 * s, kWarps);
+      w4::mbar_init(bar_full + 8 * s, 32);        // every producer lane (each stored group words)
+      w4::mbar_init(bar_empty + 8 * s, kThreads);  // every consumer thread
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -577,15 +577,16 @@ __global__ void __launch_bounds__(kRingThreads, 2) gemm_w8_ring_kernel(const GPa
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (j < nj) w4::sts32(st + kRingChunk + (t + 32 * j) * 4, szr[j]);
-        __syncwarp();
         if (t == 0) {
           const int u0 = c * UC;
           const int nu = min(UC, n_units - u0);
           const uint32_t bytes = (uint32_t)nu * 128u * NWT;
-          w4::mbar_expect_tx(bar_full + 8 * s, bytes * NT);  // release: the group words above are visible with the chunk
+          w4::mbar_expect_tx(bar_full + 8 * s, bytes * NT);
 #pragma unroll
           for (int h = 0; h < NT; ++h)
             w4::bulk_g2s(st + h * SUB, p.w + ((int64_t)(rt * NT + h) * n_units + u0) * 32 * NWT, bytes, bar_full + 8 * s, pol);
+        } else {
+          mbar_arrive(bar_full + 8 * s);  // release: this lane's group words are visible with the chunk
         }
         int nrt = rt, nc = c + 1;
         if (nc == n_chunks) nc = 0, nrt = rt + (int)gridDim.x;
@@ -680,8 +681,7 @@ __global__ void __launch_bounds__(kRingThreads, 2) gemm_w8_ring_kernel(const GPa
           }
         }
       }
-      __syncwarp();
-      if (t == 0) mbar_arrive(bar_empty + 8 * s);
+      mbar_arrive(bar_empty + 8 * s);
       if (++s == stages) s = 0, ph ^= 1;
     }
 
@@ -812,11 +812,12 @@ int launch(const GParams& p, cudaStream_t st) {
   if (KIND == W16 && ALAYOUT) return launch_stream<DT, KIND, ALAYOUT, 1>(p, st);  // no inner k in this layout
   if constexpr (KIND == W8) {
     int rc = TG_ERR_UNSUPPORTED;
-    switch (p.ik) {
+    switch (p.ik) {  // the inner-k values the int8 layouts exist in (capi.cu): 1, 2 and - B layout only - 4
       case 1: rc = launch_ring<DT, ALAYOUT, 1>(p, st); break;
       case 2: rc = launch_ring<DT, ALAYOUT, 2>(p, st); break;
-      case 4: rc = launch_ring<DT, ALAYOUT, 4>(p, st); break;
-      case 8: rc = launch_ring<DT, ALAYOUT, 8>(p, st); break;
+      case 4:
+        if constexpr (!ALAYOUT) rc = launch_ring<DT, ALAYOUT, 4>(p, st);
+        break;
     }
     if (rc != TG_ERR_UNSUPPORTED) return rc;
   }

@@ -49,6 +49,35 @@ def test_gemm_matches_oracle(case, cuda_device):
     assert (ulp == 0).double().mean().item() >= 0.95
 
 
+def _int8_case(i, **kw):
+    return dict(kind="gemm", seed=9100 + i, fmt="int8", api="RM", x_ik=1, **kw)
+
+
+# The int8 ring kernel (csrc/gemv_generic.cu gemm_w8_ring_kernel): several chunks per row tile, a partial last chunk,
+# every inner-k / group size, two passes of activation rows, more row tiles than resident CTAs (ring wrap-around and
+# the double-buffered partial sums), and a B-layout row count that is not a multiple of 16 (stream-kernel fallback).
+INT8_RING_CASES = [_int8_case(i, **kw) for i, kw in enumerate([
+    dict(dt="bf16", side="right", m=1, n=64, k=4096, g=128, ik=4),
+    dict(dt="fp16", side="right", m=8, n=48, k=2112, g=64, ik=4),
+    dict(dt="bf16", side="right", m=9, n=32, k=1024, g=32, ik=4),
+    dict(dt="bf16", side="right", m=16, n=40, k=1024, g=256, ik=2),
+    dict(dt="fp16", side="right", m=2, n=16, k=1056, g=32, ik=1),
+    dict(dt="bf16", side="right", m=5, n=80, k=3072, g=256, ik=2),
+    dict(dt="bf16", side="right", m=2, n=16 * (2 * 148 + 5), k=1024, g=128, ik=4),
+    dict(dt="bf16", side="right", m=3, n=32, k=1056, g=32, ik=2),
+    dict(dt="bf16", side="left", m=3, n=48, k=3072, g=128, ik=1),
+    dict(dt="fp16", side="left", m=8, n=16, k=1184, g=32, ik=2),
+    dict(dt="bf16", side="left", m=12, n=32, k=2048, g=64, ik=2),
+    dict(dt="bf16", side="left", m=1, n=64, k=2304, g=256, ik=1),
+    dict(dt="fp16", side="left", m=4, n=16 * (2 * 148 + 3), k=512, g=128, ik=2),
+])]
+
+
+@pytest.mark.parametrize("case", INT8_RING_CASES, ids=[C.case_id(c) for c in INT8_RING_CASES])
+def test_int8_ring_kernel_matches_oracle(case, cuda_device):
+    test_gemm_matches_oracle(case, cuda_device)
+
+
 @pytest.mark.parametrize("dt", ["bf16", "fp16"])
 @pytest.mark.parametrize("fmt", ["int4", "any4g", "mx4", "int8"])
 @pytest.mark.parametrize("side", ["right", "left"])
