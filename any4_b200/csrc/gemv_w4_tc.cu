@@ -1213,7 +1213,10 @@ int launch_one(ParamsTC p, const Peers& peers, int row_blocks, cudaStream_t st) 
   const int S = p.stages_per_row;
   const int64_t stages = (int64_t)row_blocks * S;
   int per_sm = g_ctas_per_sm;
-  if (per_sm <= 0) per_sm = (stages >= (int64_t)di->n_sm * 2 * 5 || row_blocks > di->n_sm) ? 2 : 1;  // (6144 x 4096: 8.4 -> 6.7 us)
+  // measured, one activation row, homogeneous chains (us, 1 / 2 CTAs per SM): 6144 x 4096 8.4 / 6.7; 4096 x 6144 8.1 / 7.1;
+  // 4096 x 8192 10.3 / 9.2; 4096 x 11008 13.9 / 11.0 - but 4096 x 4096 5.6 / 6.0; 4096 x 5120 6.9 / 7.7; 2048 x 14336 9.2 / 9.7
+  if (per_sm <= 0)
+    per_sm = (stages >= (int64_t)di->n_sm * 2 * 5 || row_blocks > di->n_sm || (row_blocks >= 128 && stages >= (int64_t)di->n_sm * 5)) ? 2 : 1;
   if (per_sm > C::kMinBlocks) per_sm = C::kMinBlocks;
   int64_t slots = (int64_t)di->n_sm * per_sm;
   if (slots > kMaxGrid) slots = kMaxGrid;
