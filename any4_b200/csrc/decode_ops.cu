@@ -310,11 +310,28 @@ rope_attn_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ 
 // weights) streams its weights and fills its first tensor-memory slots while these loads cross PCIe.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1) stage_host_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n16) {
-  pdl_prologue();
-  for (int i = (int)threadIdx.x; i < n16; i += 256) {
-    uint4 v;
-    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
-    dst[i] = v;
+  // x_host is an INPUT written by the host: its first 16 KiB are fetched over PCIe (the slow part, ~2 us) before the
+  // previous kernel of the stream has finished; only the staging buffer, which that kernel may still be reading, is
+  // ordered behind it.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  constexpr int kPre = 4;
+  uint4 v[kPre];
+#pragma unroll
+  for (int j = 0; j < kPre; ++j) {
+    const int i = (int)threadIdx.x + 256 * j;
+    if (i < n16)
+      asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "l"(src + i) : "memory");
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < kPre; ++j) {
+    const int i = (int)threadIdx.x + 256 * j;
+    if (i < n16) dst[i] = v[j];
+  }
+  for (int i = (int)threadIdx.x + 256 * kPre; i < n16; i += 256) {
+    uint4 w;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(src + i) : "memory");
+    dst[i] = w;
   }
 }
 

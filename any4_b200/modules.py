@@ -207,7 +207,9 @@ class Any4Linear(_PackedLinear):
         outputs straight into the pinned host buffer - no copy-engine transfers, no output staging; the GEMV's weight
         stream runs while the activations cross PCIe.  (They are staged because every CTA reads all of them: from the
         device they come out of L2, from host memory each read would cross PCIe.)  All argument checks happen here,
-        once.  Synchronize the stream before reading `out`; refill `input` in place between launches.
+        once.  Synchronize the stream before reading `out`; refill `input` in place between launches - from the HOST,
+        after that synchronize: the staging kernel fetches `input` as soon as it starts, possibly while earlier work of
+        the stream is still running, so `input` must not be written by device work of the same stream.
         Weight-on-the-right kernel, packed weight, no bias."""
         import ctypes
 

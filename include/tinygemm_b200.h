@@ -160,7 +160,10 @@ int tg_repack_Aint4_to_Bint4(const int32_t* in, int32_t* out, int64_t rows, int6
  * (no counterpart in the reference, whose ops take device tensors): one tiny kernel pulls `x_host` (device-accessible
  * pinned memory, unified addressing) into the device buffer `x_staging` [rows_x][k], the GEMV - ordered behind it by
  * programmatic dependent launch, its weight stream already running - writes its outputs straight to `y_host`.  Two
- * kernel launches from ONE call, no copy-engine transfers.  (x is staged because every CTA reads all of it.) */
+ * kernel launches from ONE call, no copy-engine transfers.  (x is staged because every CTA reads all of it.)
+ * `x_host` is an input the HOST wrote before the call: with TG_OPT_PDL the staging kernel fetches it while the previous
+ * kernel of the stream may still be running (only `x_staging` and `y_host` are ordered behind that kernel), so it must
+ * not be the output of earlier device work on the same stream - stage such data with a device-side copy instead. */
 int tg_gemm_w4_rm_hostio(void* y_host, const void* x_host, void* x_staging, const int32_t* w, const void* scales_zeros,
                          const void* lut, const uint8_t* exponents, int64_t rows_x, int64_t w_rows, int64_t k, int group,
                          int inner_k_tiles, tg_w4_format format, tg_weight_side side, tg_dtype dtype, void* stream);
