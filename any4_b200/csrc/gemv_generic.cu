@@ -5,11 +5,14 @@
 // (reference: TinyGemmImpl.cuh:23-345, MatrixLayoutA.cuh:211-373, :818-1062, MatrixLayoutB.cuh:461-684,
 // :1103-1328, Dequantization.cuh:265-328).
 //
-// gemm_stream_kernel (default): the packed layouts are mma.m16n8k16 fragment orders, and the words a lane owns for IK
-// consecutive k-tiles are contiguous.  A CTA (8 warps splitting k) walks over row tiles (persistent grid), stages the
-// activations once in shared memory, fetches U units per lane with 16-byte loads before decoding any of them, decodes
-// int8 with bit patterns + one exact HSUB2 + the reference's single-rounded FMA, and feeds the words straight into
-// mma.sync (fp32 accumulation of exact products).  Warps are combined through shared memory, one RN at the end.
+// gemm_w8_ring_kernel (int8): producer-warp bulk-TMA ring, weights as the 16-row mma operand (a PAIR of B-layout tiles
+// is one A fragment), group words travelling with the stage, byte-permute decode; see the comment above the kernel.
+// gemm_stream_kernel (16-bit weights; int8 shapes the ring kernel does not take): the packed layouts are mma.m16n8k16
+// fragment orders, and the words a lane owns for IK consecutive k-tiles are contiguous.  A CTA (8 warps splitting k)
+// walks over row tiles (persistent grid), stages the activations once in shared memory, fetches U units per lane with
+// 16-byte loads before decoding any of them, decodes int8 with bit patterns + one exact HSUB2 + the reference's
+// single-rounded FMA, and feeds the words straight into mma.sync (fp32 accumulation of exact products).  Warps are
+// combined through shared memory, one RN at the end.
 // gemm_frag_kernel: the simple per-k-tile FFMA version, kept for k too long to stage the activations.
 #include <cstdlib>
 
