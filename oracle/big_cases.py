@@ -81,6 +81,48 @@ def run_ops(c, device="cuda:0"):
     return y[:, sample_cols(n).to(device)].cpu()
 
 
+# ---- int8 and 16-bit weights at the headline sizes (tests/golden/golden_big_w8.npz) ----
+W8_SHAPES = [(4096, 4096), (8192, 8192), (4096, 11008)]
+
+
+def cases_w8():
+    out = []
+    for (n, k) in W8_SHAPES:
+        for side in ("right", "left"):
+            for m in (1, 8, 16):
+                out.append(dict(fmt="int8", side=side, n=n, k=k, m=m))
+    for m in (1, 16):
+        out.append(dict(fmt="f16", side="right", n=4096, k=4096, m=m))
+    return out
+
+
+@functools.lru_cache(maxsize=1)
+def shape_inputs_w8(n, k):
+    gen = torch.Generator().manual_seed(n * 37 + k + 1)
+    words = torch.randint(-2**31, 2**31 - 1, (n * k // 4,), generator=gen, dtype=torch.int64).to(torch.int32)
+    sz = torch.stack([torch.rand(k // G, n, generator=gen) * 0.01 + 0.001, torch.randn(k // G, n, generator=gen) * 0.01],
+                     dim=2).bfloat16().contiguous()
+    x = torch.randn(16, k, generator=gen).bfloat16()
+    w16 = torch.randn(n // 8, k // 32, 32, 8, generator=gen).bfloat16() if n * k <= 4096 * 4096 else None
+    return dict(words=words, sz=sz, x=x, w16=w16)
+
+
+def run_ops_w8(c, device="cuda:0"):
+    """int8: B layout inner-k 4 [n/8][k/64][32][4], A layout inner-k 2 [n/16][k/32][32][4]; 16-bit: B layout inner-k 2."""
+    ops = torch.ops.tinygemm
+    n, k, m = c["n"], c["k"], c["m"]
+    s = shape_inputs_w8(n, k)
+    right = c["side"] == "right"
+    x = s["x"][:m].contiguous().to(device)
+    if c["fmt"] == "f16":
+        y = ops.tinygemm_y_f16RM_x_f16RM_w_f16TC(x, s["w16"].to(device), True)
+    else:
+        w = s["words"].to(device).view(n // 8, k // 64, 32, 4) if right else s["words"].to(device).view(n // 16, k // 32, 32, 4)
+        a, b = (x, w) if right else (w, x)
+        y = ops.tinygemm_y_f16RM_x_f16RM_w_int8TC(a, b, G, s["sz"].to(device), right)
+    return y[:, sample_cols(n).to(device)].cpu()
+
+
 def to_u16(t):
     return t.contiguous().view(torch.int16).numpy().view(np.uint16)
 

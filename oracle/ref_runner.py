@@ -5,6 +5,7 @@ TEST INFRASTRUCTURE ONLY.  Must be its own process: the reference registers the 
 
   python oracle/ref_runner.py golden <out.npz>      evaluate every parity case (oracle/cases.py)
   python oracle/ref_runner.py golden_big <out.npz>  the headline-size cases (oracle/big_cases.py), sampled columns
+  python oracle/ref_runner.py golden_big_w8 <out.npz>  the same for int8 / 16-bit weights (cases_w8)
   python oracle/ref_runner.py bench <n> <k> <iters> time the reference any4 GEMV (rotating copies)
   python oracle/ref_runner.py sweep                 the format x m sweep of bench.py (4096^2) on the reference kernels
 """
@@ -58,6 +59,23 @@ def golden_big(out_path):
     for c in B.cases():
         try:
             y = B.run_ops(c, "cuda:0")
+        except RuntimeError as e:
+            print(f"[ref] {B.case_id(c)} rejected by the reference: {str(e).splitlines()[0][:120]}")
+            continue
+        out[B.case_id(c)] = B.to_u16(y)
+    np.savez_compressed(out_path, **out)
+    print(f"[ref] wrote {out_path}: {len(out)} arrays")
+
+
+def golden_big_w8(out_path):
+    """int8 / 16-bit weights at the headline sizes (oracle/big_cases.py cases_w8): sampled output columns."""
+    from oracle import big_cases as B
+
+    load_reference()
+    out = {}
+    for c in B.cases_w8():
+        try:
+            y = B.run_ops_w8(c, "cuda:0")
         except RuntimeError as e:
             print(f"[ref] {B.case_id(c)} rejected by the reference: {str(e).splitlines()[0][:120]}")
             continue
@@ -176,5 +194,7 @@ if __name__ == "__main__":
         golden(sys.argv[2])
     elif sys.argv[1] == "golden_big":
         golden_big(sys.argv[2])
+    elif sys.argv[1] == "golden_big_w8":
+        golden_big_w8(sys.argv[2])
     elif sys.argv[1] == "bench":
         bench(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))

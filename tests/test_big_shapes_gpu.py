@@ -42,6 +42,31 @@ def test_headline_shape_matches_reference_kernel(case, cuda_device):
     assert _tol.frob_rel(y, ref) <= _tol.FROB_REL  # the north-star tolerance: 1e-3 relative
 
 
+GOLD_W8_PATH = os.path.join(os.path.dirname(__file__), "golden", "golden_big_w8.npz")
+GOLD_W8 = np.load(GOLD_W8_PATH) if os.path.exists(GOLD_W8_PATH) else None
+CASES_W8 = B.cases_w8()
+
+
+@pytest.mark.skipif(GOLD_W8 is None, reason="golden_big_w8.npz not generated yet")
+@pytest.mark.parametrize("case", CASES_W8, ids=[B.case_id(c) for c in CASES_W8])
+def test_headline_shape_w8_matches_reference_kernel(case, cuda_device):
+    """int8 (ring kernel: both layouts, one pass and two passes of activation rows, 4 / 8 / 10.75 chunks per row tile)
+    and 16-bit weights at the headline sizes against sampled outputs of the reference's kernels
+    (`oracle/ref_runner.py golden_big_w8`)."""
+    import tinygemm  # noqa: F401
+
+    name = B.case_id(case)
+    if name not in GOLD_W8:
+        pytest.skip("case not in the golden file (rejected by the reference)")
+    ref = B.from_u16(GOLD_W8[name])
+    y = B.run_ops_w8(case, cuda_device)
+    assert y.shape == ref.shape and y.dtype == torch.bfloat16
+    assert torch.isfinite(y.float()).all()
+    frac = (dequant.ulp_distance(y, ref) == 0).double().mean().item()
+    assert frac >= 0.95, f"only {frac:.3f} bit-equal to the reference kernel"
+    assert _tol.frob_rel(y, ref) <= _tol.FROB_REL
+
+
 @pytest.mark.parametrize("fmt", ["any4r", "int4", "mx4"])
 def test_headline_shape_matches_oracle(fmt, cuda_device):
     """The sampled columns of the 4096^2 m = 4 case against the float64 CPU restatement (independent of the golden)."""
