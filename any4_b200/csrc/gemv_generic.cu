@@ -524,16 +524,18 @@ __device__ __forceinline__ void decode8_word(uint32_t word, uint32_t s_lo, uint3
   }
 }
 
-template <tg_dtype DT, bool ALAYOUT, int IK>
+template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK>
 __global__ void __launch_bounds__(kRingThreads, 2) gemm_w8_ring_kernel(const GParams p, int kpad, int static_w, int stages) {
+  static_assert(KIND == W8 || KIND == W16, "int8 or 16-bit weights");
   constexpr int ROWS = 16;                       // weight rows per item: one A-layout tile, or two adjacent B-layout tiles
   constexpr int NT = ALAYOUT ? 1 : 2;            // packed tiles per item
-  constexpr int NWT = ALAYOUT ? 2 * IK : IK;     // words per lane per unit of one packed tile
+  constexpr int WKT = (KIND == W8 ? 1 : 2) * (ALAYOUT ? 2 : 1);  // words per lane per k-tile of one packed tile
+  constexpr int NWT = WKT * IK;                  // ... per unit
   constexpr int SUB = kRingChunk / NT;           // bytes of one packed tile per stage
-  constexpr int UC = SUB / (128 * NWT);          // units per chunk (= 64 / IK)
+  constexpr int UC = SUB / (128 * NWT);          // units per chunk
   constexpr int UPW = UC / kWarps;               // units per warp per chunk
-  constexpr int CK = UC * IK * 16;               // k per chunk
-  static_assert(UPW >= 1 && UPW * NT * NWT == 16 && CK == 1024, "a warp owns 16 words per lane per chunk");
+  constexpr int CK = UC * IK * 16;               // k per chunk: 1024 (int8) / 512 (16-bit)
+  static_assert(UPW >= 1 && UPW * NT * NWT == 16 && CK == (KIND == W8 ? 1024 : 512), "a warp owns 16 words per lane per chunk");
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const uint32_t base = w4::smem_u32(ring_smem);
   const uint32_t bar_full = base, bar_empty = base + 8 * kRingMaxStages, stage0 = base + kRingCtrl;
@@ -560,7 +562,8 @@ __global__ void __launch_bounds__(kRingThreads, 2) gemm_w8_ring_kernel(const GPa
   if (warp == kWarps) {  // ---- producer ----
     if (!static_w) asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint64_t pol = w4::l2_evict_first_policy();
-    const int nj = (gc * ROWS) >> 5;  // group words per lane per chunk: 16 / 8 / 4 / 2 for groups of 32 / 64 / 128 / 256
+    // group words per lane per chunk: 16 / 8 / 4 / 2 for groups of 32 / 64 / 128 / 256 (none for 16-bit weights)
+    const int nj = KIND == W8 ? (gc * ROWS) >> 5 : 0;
     uint32_t szr[16];
     auto load_sz = [&](int rt, int c) {
 #pragma unroll
@@ -665,12 +668,19 @@ __global__ void __launch_bounds__(kRingThreads, 2) gemm_w8_ring_kernel(const GPa
               z2[h] = __byte_perm(v, 0, 0x3232);
             }
           };
-          if (one_group_per_unit) group_words(ul * IK * 16);
+          if (KIND == W8 && one_group_per_unit) group_words(ul * IK * 16);
 #pragma unroll
           for (int ki = 0; ki < IK; ++ki) {
-            if (!one_group_per_unit) group_words((ul * IK + ki) * 16);
+            if (KIND == W8 && !one_group_per_unit) group_words((ul * IK + ki) * 16);
             uint32_t a0, a1, a2, a3;
-            if constexpr (ALAYOUT) {  // word 0: (row g, row g + 8) at k 2q..2q+1, word 1: the same rows at k + 8
+            if constexpr (KIND == W16) {
+              if constexpr (ALAYOUT) {  // the four words ARE the fragment
+                a0 = raw[j][4 * ki], a1 = raw[j][4 * ki + 1], a2 = raw[j][4 * ki + 2], a3 = raw[j][4 * ki + 3];
+              } else {                  // (b0, b1) of the first tile: row g at (k, k + 8); of the second tile: row g + 8
+                a0 = raw[j][2 * ki], a2 = raw[j][2 * ki + 1];
+                a1 = raw[j][NWT + 2 * ki], a3 = raw[j][NWT + 2 * ki + 1];
+              }
+            } else if constexpr (ALAYOUT) {  // word 0: (row g, row g + 8) at k 2q..2q+1, word 1: the same rows at k + 8
               decode8_word<DT>(raw[j][2 * ki], s2[0], z2[0], s2[1], z2[1], a0, a1);
               decode8_word<DT>(raw[j][2 * ki + 1], s2[0], z2[0], s2[1], z2[1], a2, a3);
             } else {                  // a word of the first tile: row g at (k, k + 8); of the second: row g + 8
@@ -754,7 +764,7 @@ int launch_stream(const GParams& p, cudaStream_t st) {
 
 // int8 through the ring kernel, in passes of up to 8 activation rows (the weight of a second pass usually comes from
 // L2): TG_OK / TG_ERR_UNSUPPORTED (use the stream kernel)
-template <tg_dtype DT, bool ALAYOUT, int IK>
+template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK>
 int launch_ring(const GParams& p0, cudaStream_t st) {
   static const int enabled = [] { const char* e = getenv("TG_W8_RING"); return e ? atoi(e) : 1; }();
   static const int ctas_env = [] { const char* e = getenv("TG_W8_CTAS"); return e ? atoi(e) : 0; }();
@@ -763,9 +773,9 @@ int launch_ring(const GParams& p0, cudaStream_t st) {
   int per_pass = (int)((size_t)kRingMaxX / row_bytes);
   if (per_pass > 8) per_pass = 8;
   if (!enabled || per_pass < 1 || (p0.w_rows & 15) != 0 || (reinterpret_cast<uintptr_t>(p0.w) & 15) != 0 ||
-      (reinterpret_cast<uintptr_t>(p0.sz) & 3) != 0)
+      (KIND == W8 && (reinterpret_cast<uintptr_t>(p0.sz) & 3) != 0))
     return TG_ERR_UNSUPPORTED;
-  auto kern = gemm_w8_ring_kernel<DT, ALAYOUT, IK>;
+  auto kern = gemm_w8_ring_kernel<DT, KIND, ALAYOUT, IK>;
   static thread_local int ready[kMaxDevices] = {}, n_sm = 0;
   int& rdy = ready[current_device_slot()];
   if (!rdy) {
@@ -812,18 +822,21 @@ int launch_ring(const GParams& p0, cudaStream_t st) {
 
 template <tg_dtype DT, Kind KIND, bool ALAYOUT>
 int launch(const GParams& p, cudaStream_t st) {
-  if (KIND == W16 && ALAYOUT) return launch_stream<DT, KIND, ALAYOUT, 1>(p, st);  // no inner k in this layout
-  if constexpr (KIND == W8) {
+  if constexpr (KIND == W8 || KIND == W16) {
+    // the inner-k values the layouts exist in (capi.cu): int8 1, 2 and - B layout only - 4; 16-bit 1 and - B layout only - 2
     int rc = TG_ERR_UNSUPPORTED;
-    switch (p.ik) {  // the inner-k values the int8 layouts exist in (capi.cu): 1, 2 and - B layout only - 4
-      case 1: rc = launch_ring<DT, ALAYOUT, 1>(p, st); break;
-      case 2: rc = launch_ring<DT, ALAYOUT, 2>(p, st); break;
+    switch (KIND == W16 && ALAYOUT ? 1 : p.ik) {
+      case 1: rc = launch_ring<DT, KIND, ALAYOUT, 1>(p, st); break;
+      case 2:
+        if constexpr (KIND == W8 || !ALAYOUT) rc = launch_ring<DT, KIND, ALAYOUT, 2>(p, st);
+        break;
       case 4:
-        if constexpr (!ALAYOUT) rc = launch_ring<DT, ALAYOUT, 4>(p, st);
+        if constexpr (KIND == W8 && !ALAYOUT) rc = launch_ring<DT, KIND, ALAYOUT, 4>(p, st);
         break;
     }
     if (rc != TG_ERR_UNSUPPORTED) return rc;
   }
+  if (KIND == W16 && ALAYOUT) return launch_stream<DT, KIND, ALAYOUT, 1>(p, st);  // no inner k in this layout
   switch (p.ik) {
     case 1: return launch_stream<DT, KIND, ALAYOUT, 1>(p, st);
     case 2: return launch_stream<DT, KIND, ALAYOUT, 2>(p, st);

@@ -78,6 +78,24 @@ def test_int8_ring_kernel_matches_oracle(case, cuda_device):
     test_gemm_matches_oracle(case, cuda_device)
 
 
+# the same kernel with 16-bit weights (512 k per chunk, no group words)
+F16_RING_CASES = [dict(kind="gemm", seed=9200 + i, fmt="f16", api="RM", x_ik=1, g=0, **kw) for i, kw in enumerate([
+    dict(dt="bf16", side="right", m=1, n=64, k=4096, ik=2),
+    dict(dt="fp16", side="right", m=8, n=48, k=2112, ik=2),
+    dict(dt="bf16", side="right", m=9, n=32, k=1056, ik=1),
+    dict(dt="bf16", side="right", m=16, n=40, k=1024, ik=2),           # 40 rows: stream-kernel fallback
+    dict(dt="bf16", side="right", m=2, n=16 * (2 * 148 + 5), k=512, ik=2),
+    dict(dt="bf16", side="left", m=3, n=48, k=3072, ik=1),
+    dict(dt="fp16", side="left", m=12, n=32, k=1184, ik=1),
+    dict(dt="bf16", side="left", m=4, n=16 * (2 * 148 + 3), k=256, ik=1),
+])]
+
+
+@pytest.mark.parametrize("case", F16_RING_CASES, ids=[C.case_id(c) for c in F16_RING_CASES])
+def test_f16_ring_kernel_matches_oracle(case, cuda_device):
+    test_gemm_matches_oracle(case, cuda_device)
+
+
 @pytest.mark.parametrize("dt", ["bf16", "fp16"])
 @pytest.mark.parametrize("fmt", ["int4", "any4g", "mx4", "int8"])
 @pytest.mark.parametrize("side", ["right", "left"])
