@@ -524,8 +524,8 @@ __device__ __forceinline__ void decode8_word(uint32_t word, uint32_t s_lo, uint3
   }
 }
 
-template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK>
-__global__ void __launch_bounds__(kRingThreads, 2) gemm_w8_ring_kernel(const GParams p, int kpad, int static_w, int stages) {
+template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK, bool HI>  // HI: activation rows 8..15 of the pass exist (second mma per fragment)
+__global__ void __launch_bounds__(kRingThreads, HI ? 1 : 2) gemm_w8_ring_kernel(const GParams p, int kpad, int static_w, int stages) {
   static_assert(KIND == W8 || KIND == W16, "int8 or 16-bit weights");
   constexpr int ROWS = 16;                       // weight rows per item: one A-layout tile, or two adjacent B-layout tiles
   constexpr int NT = ALAYOUT ? 1 : 2;            // packed tiles per item
@@ -628,16 +628,18 @@ __global__ void __launch_bounds__(kRingThreads, 2) gemm_w8_ring_kernel(const GPa
   const int na = p.rows_x;
   const bool has_x = g < na;  // this lane's activation row (B operand column g)
   const uint32_t x_lane = w4::smem_u32(xs) + ((has_x ? g : 0) * (kpad + 8) + 2 * q) * 2;
+  const bool has_xh = HI && g + 8 < na;  // ... and row g + 8 of a 9..16-row pass
+  const uint32_t x_lane_h = w4::smem_u32(xs) + ((has_xh ? g + 8 : 0) * (kpad + 8) + 2 * q) * 2;
   const bool one_group_per_unit = (1 << p.glog2) >= IK * 16;
 
   int s = 0, buf = 0;
   uint32_t ph = 0;
   for (int rt = blockIdx.x; rt < n_items; rt += gridDim.x, buf ^= 1) {
-    float acc[2][4];
+    float acc[2][4], acch[2][4];  // (acch: rows 8..15 of the pass, HI only)
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+      for (int i = 0; i < 4; ++i) acc[c][i] = 0.f, acch[c][i] = 0.f;
 
     for (int c = 0; c < n_chunks; ++c) {
       const uint32_t st = stage0 + s * kRingStageBytes;
@@ -691,6 +693,12 @@ __global__ void __launch_bounds__(kRingThreads, 2) gemm_w8_ring_kernel(const GPa
             const uint32_t x0 = has_x ? w4::lds32(xa) : 0u;
             const uint32_t x1 = has_x ? w4::lds32(xa + 16) : 0u;
             w4::mma16816<DT>(acc[(ki + j) & 1], a0, a1, a2, a3, x0, x1);
+            if constexpr (HI) {
+              const uint32_t xh = x_lane_h + (uint32_t)((u0 + ul) * IK + ki) * 32;
+              const uint32_t x2 = has_xh ? w4::lds32(xh) : 0u;
+              const uint32_t x3 = has_xh ? w4::lds32(xh + 16) : 0u;
+              w4::mma16816<DT>(acch[(ki + j) & 1], a0, a1, a2, a3, x2, x3);
+            }
           }
         }
       }
@@ -698,18 +706,24 @@ __global__ void __launch_bounds__(kRingThreads, 2) gemm_w8_ring_kernel(const GPa
       if (++s == stages) s = 0, ph ^= 1;
     }
 
-    float* rb = red + buf * (kWarps * 4 * 32);
+    // cross-warp sums, rows 0..7 and (HI) 8..15 of the pass one after the other.  The scratch is double-buffered: the
+    // buffer written two reductions ago was read before the barrier of the previous one.
 #pragma unroll
-    for (int i = 0; i < 4; ++i) rb[(warp * 4 + i) * 32 + t] = acc[0][i] + acc[1][i];
-    consumer_barrier();  // (the buffer written two tiles ago was read before the barrier of the previous tile)
-    if (threadIdx.x < 128) {
-      // C fragment: c0, c1 = (weight row g, activation rows 2q, 2q + 1), c2, c3 = (weight row g + 8, ...)
-      const int ci = threadIdx.x >> 5;
-      float sum = 0.f;
+    for (int half = 0; half < (HI ? 2 : 1); ++half) {
+      float* rb = red + buf * (kWarps * 4 * 32);
 #pragma unroll
-      for (int w2 = 0; w2 < kWarps; ++w2) sum += rb[(w2 * 4 + ci) * 32 + t];
-      const int wrow = g + 8 * (ci >> 1), act = 2 * q + (ci & 1);
-      if (act < na) p.y[(int64_t)act * p.w_rows + rt * ROWS + wrow] = from_f32<DT>(sum);
+      for (int i = 0; i < 4; ++i) rb[(warp * 4 + i) * 32 + t] = half == 0 ? acc[0][i] + acc[1][i] : acch[0][i] + acch[1][i];
+      consumer_barrier();
+      if (threadIdx.x < 128) {
+        // C fragment: c0, c1 = (weight row g, activation rows 2q, 2q + 1), c2, c3 = (weight row g + 8, ...)
+        const int ci = threadIdx.x >> 5;
+        float sum = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < kWarps; ++w2) sum += rb[(w2 * 4 + ci) * 32 + t];
+        const int wrow = g + 8 * (ci >> 1), act = 2 * q + (ci & 1) + 8 * half;
+        if (act < na) p.y[(int64_t)act * p.w_rows + rt * ROWS + wrow] = from_f32<DT>(sum);
+      }
+      if (half + 1 < (HI ? 2 : 1)) buf ^= 1;
     }
   }
 }
@@ -762,20 +776,11 @@ int launch_stream(const GParams& p, cudaStream_t st) {
   return launch_stream_a<DT, KIND, ALAYOUT, IK, false>(p, rows_per_pass, kpad, st);
 }
 
-// int8 through the ring kernel, in passes of up to 8 activation rows (the weight of a second pass usually comes from
-// L2): TG_OK / TG_ERR_UNSUPPORTED (use the stream kernel)
-template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK>
-int launch_ring(const GParams& p0, cudaStream_t st) {
-  static const int enabled = [] { const char* e = getenv("TG_W8_RING"); return e ? atoi(e) : 1; }();
-  static const int ctas_env = [] { const char* e = getenv("TG_W8_CTAS"); return e ? atoi(e) : 0; }();
-  const int kpad = p0.outer_k * IK * 16;
-  const size_t row_bytes = (size_t)(kpad + 8) * 2;
-  int per_pass = (int)((size_t)kRingMaxX / row_bytes);
-  if (per_pass > 8) per_pass = 8;
-  if (!enabled || per_pass < 1 || (p0.w_rows & 15) != 0 || (reinterpret_cast<uintptr_t>(p0.w) & 15) != 0 ||
-      (KIND == W8 && (reinterpret_cast<uintptr_t>(p0.sz) & 3) != 0))
-    return TG_ERR_UNSUPPORTED;
-  auto kern = gemm_w8_ring_kernel<DT, KIND, ALAYOUT, IK>;
+// int8 / 16-bit weights through the ring kernel, in passes of up to 16 activation rows (the weight of a second pass
+// usually comes from L2): TG_OK / TG_ERR_UNSUPPORTED (use the stream kernel)
+template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK, bool HI>
+int launch_ring_pass(const GParams& p, int kpad, size_t xbytes, int ctas_env, cudaStream_t st) {
+  auto kern = gemm_w8_ring_kernel<DT, KIND, ALAYOUT, IK, HI>;
   static thread_local int ready[kMaxDevices] = {}, n_sm = 0;
   int& rdy = ready[current_device_slot()];
   if (!rdy) {
@@ -789,33 +794,53 @@ int launch_ring(const GParams& p0, cudaStream_t st) {
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
     rdy = 1;
   }
-  const int items = p0.w_rows / 16;
+  const int items = p.w_rows / 16;
+  // two CTAs per SM while four stages + the activations fit 113 KiB, one (with the whole 227 KiB) beyond that
+  int per_sm = ctas_env > 0 ? ctas_env : (ring_fixed_bytes(kRingMaxStages) + xbytes <= 113 * 1024 ? 2 : 1);
+  if (HI) per_sm = 1;
+  const int slots = per_sm * n_sm;  // persistent: the resident CTAs walk over the row tiles
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(items < slots ? items : slots), 1, 1);
+  cfg.blockDim = dim3(kRingThreads, 1, 1);
+  cfg.dynamicSmemBytes = ring_fixed_bytes(kRingMaxStages) + xbytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = w4::g_pdl ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, kpad, (int)(w4::g_static_weights ? 1 : 0), (int)kRingMaxStages);
+  if (e != cudaSuccess) {
+    set_error("gemm_w8_ring_kernel launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return TG_ERR_CUDA;
+  }
+  count_launch();
+  return TG_OK;
+}
+
+template <tg_dtype DT, Kind KIND, bool ALAYOUT, int IK>
+int launch_ring(const GParams& p0, cudaStream_t st) {
+  static const int enabled = [] { const char* e = getenv("TG_W8_RING"); return e ? atoi(e) : 1; }();
+  static const int ctas_env = [] { const char* e = getenv("TG_W8_CTAS"); return e ? atoi(e) : 0; }();
+  static const int rows_env = [] { const char* e = getenv("TG_W8_ROWS"); return e ? atoi(e) : 16; }();  // rows per pass (tuning)
+  const int kpad = p0.outer_k * IK * 16;
+  const size_t row_bytes = (size_t)(kpad + 8) * 2;
+  int per_pass = (int)((size_t)kRingMaxX / row_bytes);
+  const int cap = rows_env >= 1 && rows_env <= 16 ? rows_env : 16;
+  if (per_pass > cap) per_pass = cap;
+  if (!enabled || per_pass < 1 || (p0.w_rows & 15) != 0 || (reinterpret_cast<uintptr_t>(p0.w) & 15) != 0 ||
+      (KIND == W8 && (reinterpret_cast<uintptr_t>(p0.sz) & 3) != 0))
+    return TG_ERR_UNSUPPORTED;
   for (int r0 = 0; r0 < p0.rows_x; r0 += per_pass) {
     GParams p = p0;
     p.rows_x = p0.rows_x - r0 < per_pass ? p0.rows_x - r0 : per_pass;
     p.x = p0.x + (int64_t)r0 * p0.k;
     p.y = p0.y + (int64_t)r0 * p0.w_rows;
     const size_t xbytes = (size_t)p.rows_x * row_bytes;
-    // two CTAs per SM while four stages + the activations fit 113 KiB, one (with the whole 227 KiB) beyond that
-    const int per_sm = ctas_env > 0 ? ctas_env : (ring_fixed_bytes(kRingMaxStages) + xbytes <= 113 * 1024 ? 2 : 1);
-    const int slots = per_sm * n_sm;  // persistent: the resident CTAs walk over the row tiles
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(items < slots ? items : slots), 1, 1);
-    cfg.blockDim = dim3(kRingThreads, 1, 1);
-    cfg.dynamicSmemBytes = ring_fixed_bytes(kRingMaxStages) + xbytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = w4::g_pdl ? 1 : 0;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, kpad, (int)(w4::g_static_weights ? 1 : 0), (int)kRingMaxStages);
-    if (e != cudaSuccess) {
-      set_error("gemm_w8_ring_kernel launch failed: %s", cudaGetErrorString(e));
-      (void)cudaGetLastError();
-      return TG_ERR_CUDA;
-    }
-    count_launch();
+    const int rc = p.rows_x > 8 ? launch_ring_pass<DT, KIND, ALAYOUT, IK, true>(p, kpad, xbytes, ctas_env, st)
+                                : launch_ring_pass<DT, KIND, ALAYOUT, IK, false>(p, kpad, xbytes, ctas_env, st);
+    if (rc != TG_OK) return rc;
   }
   return TG_OK;
 }
