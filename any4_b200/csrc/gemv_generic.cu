@@ -448,7 +448,8 @@ __global__ void __launch_bounds__(kThreads, TG_STREAM_MINB) gemm_stream_kernel(c
 }
 
 // ---------------------------------------------------------------------------------------
-// Ring variant for int8 weights and up to 8 activation rows (the decode case; both layouts).
+// Ring variant for int8 and 16-bit weights, up to 16 activation rows per pass (the decode case; both layouts; HI: rows
+// 8..15 ride on a second mma per decoded fragment).
 //  * The weight is always the mma's 16-row A operand and the activations its 8-column B operand: the A layout is that
 //    fragment already; in the B layout a lane's words of two ADJACENT 8-row tiles are exactly (a0, a2) and (a1, a3) of
 //    a 16-row fragment, so a pair of tiles is processed together - one mma and one pair of activation loads per 16
